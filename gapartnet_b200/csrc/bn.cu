@@ -1,0 +1,323 @@
+// Training-mode BatchNorm1d (+ReLU, +residual) over the active rows of a sparse level, and the
+// voxel<->point row gathers.  Memory-bound elementwise/reduction kernels: float4 accesses,
+// fp64 statistics, row counts read from the device.
+//
+// Reference semantics: norm_fn = BatchNorm1d(eps=1e-4, momentum=0.1) gapartnet/network/model.py:86,
+// used after every sparse conv (backbone.py:21,29,37,78,91,153,158) with ReLU / residual-add as in
+// ResBlock.forward backbone.py:40-49; pc_feature = features[pc_voxel_id] model.py:153.
+#include "common.cuh"
+#include "../../include/gapart_b200.h"
+
+// stats: [2][C] double (sum, sumsq) -> scale/shift/mean/invstd, running stats update
+__global__ void k_bn_finalize(const double* __restrict__ stats, int C, const int* __restrict__ d_n,
+                              int max_n, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float eps, float momentum,
+                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                              float* __restrict__ scale, float* __restrict__ shift,
+                              float* __restrict__ mean_o, float* __restrict__ invstd_o) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int n = gp_rows(d_n, max_n);
+    double cnt = n > 0 ? (double)n : 1.0;
+    double mean = stats[c] / cnt;
+    double var = stats[C + c] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    float sc = g * invstd;
+    scale[c] = sc;
+    shift[c] = b - (float)mean * sc;
+    mean_o[c] = (float)mean;
+    invstd_o[c] = invstd;
+    if (running_mean && n > 0) {
+        double unbiased = n > 1 ? var * cnt / (cnt - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+extern "C" int gp_bn_finalize(const double* stats, int C, const int* d_n, int max_n,
+                              const float* gamma, const float* beta, float eps, float momentum,
+                              float* running_mean, float* running_var, float* scale, float* shift,
+                              float* mean, float* invstd, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(C > 0, "gp_bn_finalize: C <= 0");
+    k_bn_finalize<<<gp_cdiv(C, 128), 128, 0, stream>>>(stats, C, d_n, max_n, gamma, beta, eps, momentum,
+                                                       running_mean, running_var, scale, shift, mean,
+                                                       invstd);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
+// per-channel sum / sumsq of a [n, C] tensor (used when the producer is not one of our convs)
+__global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ Y, int ldy, int C,
+                                                   const int* __restrict__ d_n, int max_n,
+                                                   double* __restrict__ stats, int rows_per_block) {
+    int n = gp_rows(d_n, max_n);
+    int r0 = blockIdx.x * rows_per_block;
+    if (r0 >= n) return;
+    int r1 = min(n, r0 + rows_per_block);
+    int cpr = C >> 2, rpb = 256 / cpr;
+    int cg = threadIdx.x % cpr, rl = threadIdx.x / cpr;
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    if (rl < rpb) {
+        for (int r = r0 + rl; r < r1; r += rpb) {
+            float4 v = ldg4(Y + (size_t)r * ldy + cg * 4);
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+        }
+    }
+    extern __shared__ double sm[];  // [2][C]
+    for (int i = threadIdx.x; i < 2 * C; i += 256) sm[i] = 0.0;
+    __syncthreads();
+    if (rl < rpb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sm[cg * 4 + j], (double)s[j]);
+            atomicAdd(&sm[C + cg * 4 + j], (double)q[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(stats + i, sm[i]);
+}
+
+extern "C" int gp_col_stats(const float* Y, int ldy, int C, const int* d_n, int max_n, double* stats,
+                            void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024 && ldy % 4 == 0, "gp_col_stats: C must be a multiple of 4");
+    if (max_n == 0) return GP_OK;
+    int rows_per_block = 512;
+    k_col_stats<<<gp_cdiv(max_n, rows_per_block), 256, 2 * C * sizeof(double), stream>>>(
+        Y, ldy, C, d_n, max_n, stats, rows_per_block);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
+// out = [relu]( y*scale + shift [+ residual] )
+__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ Y, int ldy, int C,
+                                                  const int* __restrict__ d_n, int max_n,
+                                                  const float* __restrict__ scale,
+                                                  const float* __restrict__ shift,
+                                                  const float* __restrict__ res, int ldr, int relu,
+                                                  float* __restrict__ Out, int ldo) {
+    int n = gp_rows(d_n, max_n);
+    int cpr = C >> 2;
+    long long total = (long long)n * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(t / cpr), cg = (int)(t - (long long)r * cpr);
+        float4 v = ldg4(Y + (size_t)r * ldy + cg * 4);
+        float4 sc = ldg4(scale + cg * 4), sh = ldg4(shift + cg * 4);
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        if (res) {
+            float4 rr = ldg4(res + (size_t)r * ldr + cg * 4);
+            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        }
+        if (relu) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(Out + (size_t)r * ldo + cg * 4) = v;
+    }
+}
+
+#define GP_ALIGNED16(p) ((reinterpret_cast<size_t>(p) & 15) == 0)
+
+static int ew_grid(long long total_threads) {
+    long long b = (total_threads + 255) / 256;
+    long long cap = (long long)gp_num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" int gp_bn_apply(const float* Y, int ldy, int C, const int* d_n, int max_n,
+                           const float* scale, const float* shift, const float* residual, int ldr,
+                           int relu, float* Out, int ldo, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(C > 0 && C % 4 == 0 && ldy % 4 == 0 && ldo % 4 == 0 && (!residual || ldr % 4 == 0),
+                 "gp_bn_apply: channels/strides must be multiples of 4");
+    GP_CHECK_ARG(GP_ALIGNED16(Y) && GP_ALIGNED16(Out) && GP_ALIGNED16(residual) && GP_ALIGNED16(scale) &&
+                     GP_ALIGNED16(shift), "gp_bn_apply: pointers must be 16-byte aligned");
+    if (max_n == 0) return GP_OK;
+    k_bn_apply<<<ew_grid((long long)max_n * (C / 4)), 256, 0, stream>>>(Y, ldy, C, d_n, max_n, scale,
+                                                                        shift, residual, ldr, relu, Out,
+                                                                        ldo);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
+// backward pass 1: dz = dA * (A > 0) ; sums[c] += dz ; sums[C+c] += dz * xhat
+__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ dA, int lda,
+                                                       const float* __restrict__ A, int la,
+                                                       const float* __restrict__ Y, int ldy, int C,
+                                                       const int* __restrict__ d_n, int max_n,
+                                                       const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd,
+                                                       double* __restrict__ sums, int rows_per_block) {
+    int n = gp_rows(d_n, max_n);
+    int r0 = blockIdx.x * rows_per_block;
+    if (r0 >= n) return;
+    int r1 = min(n, r0 + rows_per_block);
+    int cpr = C >> 2, rpb = 256 / cpr;
+    int cg = threadIdx.x % cpr, rl = threadIdx.x / cpr;
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    if (rl < rpb) {
+        float4 mu = ldg4(mean + cg * 4), is = ldg4(invstd + cg * 4);
+        for (int r = r0 + rl; r < r1; r += rpb) {
+            float4 g = ldg4(dA + (size_t)r * lda + cg * 4);
+            if (A) {
+                float4 a = ldg4(A + (size_t)r * la + cg * 4);
+                if (!(a.x > 0.f)) g.x = 0.f;
+                if (!(a.y > 0.f)) g.y = 0.f;
+                if (!(a.z > 0.f)) g.z = 0.f;
+                if (!(a.w > 0.f)) g.w = 0.f;
+            }
+            float4 y = ldg4(Y + (size_t)r * ldy + cg * 4);
+            s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+            q[0] += g.x * (y.x - mu.x) * is.x; q[1] += g.y * (y.y - mu.y) * is.y;
+            q[2] += g.z * (y.z - mu.z) * is.z; q[3] += g.w * (y.w - mu.w) * is.w;
+        }
+    }
+    extern __shared__ double sm[];
+    for (int i = threadIdx.x; i < 2 * C; i += 256) sm[i] = 0.0;
+    __syncthreads();
+    if (rl < rpb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sm[cg * 4 + j], (double)s[j]);
+            atomicAdd(&sm[C + cg * 4 + j], (double)q[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(sums + i, sm[i]);
+}
+
+// backward pass 2: dY = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); optional dRes (+)= dz;
+// block 0 also accumulates dgamma / dbeta.
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(
+    const float* __restrict__ dA, int lda, const float* __restrict__ A, int la,
+    const float* __restrict__ Y, int ldy, int C, const int* __restrict__ d_n, int max_n,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const double* __restrict__ sums, float* __restrict__ dY, int lddy, float* __restrict__ dRes,
+    int ldres, int res_accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    int n = gp_rows(d_n, max_n);
+    if (blockIdx.x == 0 && dgamma) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            dbeta[c] += (float)sums[c];
+            dgamma[c] += (float)sums[C + c];
+        }
+    }
+    float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+    int cpr = C >> 2;
+    long long total = (long long)n * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(t / cpr), cg = (int)(t - (long long)r * cpr);
+        float4 g = ldg4(dA + (size_t)r * lda + cg * 4);
+        if (A) {
+            float4 a = ldg4(A + (size_t)r * la + cg * 4);
+            if (!(a.x > 0.f)) g.x = 0.f;
+            if (!(a.y > 0.f)) g.y = 0.f;
+            if (!(a.z > 0.f)) g.z = 0.f;
+            if (!(a.w > 0.f)) g.w = 0.f;
+        }
+        if (dRes) {
+            float4* p = reinterpret_cast<float4*>(dRes + (size_t)r * ldres + cg * 4);
+            float4 o = g;
+            if (res_accumulate) {
+                float4 e = *p;
+                o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+            }
+            *p = o;
+        }
+        float4 y = ldg4(Y + (size_t)r * ldy + cg * 4);
+        float4 mu = ldg4(mean + cg * 4), is = ldg4(invstd + cg * 4), ga = ldg4(gamma + cg * 4);
+        float sb[4], sg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sb[j] = (float)sums[cg * 4 + j] * inv_n;
+            sg[j] = (float)sums[C + cg * 4 + j] * inv_n;
+        }
+        float4 o;
+        o.x = ga.x * is.x * (g.x - sb[0] - (y.x - mu.x) * is.x * sg[0]);
+        o.y = ga.y * is.y * (g.y - sb[1] - (y.y - mu.y) * is.y * sg[1]);
+        o.z = ga.z * is.z * (g.z - sb[2] - (y.z - mu.z) * is.z * sg[2]);
+        o.w = ga.w * is.w * (g.w - sb[3] - (y.w - mu.w) * is.w * sg[3]);
+        *reinterpret_cast<float4*>(dY + (size_t)r * lddy + cg * 4) = o;
+    }
+}
+
+extern "C" int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const float* Y, int ldy,
+                         int C, const int* d_n, int max_n, const float* mean, const float* invstd,
+                         const float* gamma, double* sums, float* dY, int lddy, float* dRes, int ldres,
+                         int res_accumulate, float* dgamma, float* dbeta, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024, "gp_bn_bwd: C must be a multiple of 4");
+    GP_CHECK_ARG(lda % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && (!A || la % 4 == 0) &&
+                     (!dRes || ldres % 4 == 0),
+                 "gp_bn_bwd: strides must be multiples of 4");
+    GP_CHECK_ARG(GP_ALIGNED16(dA) && GP_ALIGNED16(A) && GP_ALIGNED16(Y) && GP_ALIGNED16(dY) &&
+                     GP_ALIGNED16(dRes) && GP_ALIGNED16(mean) && GP_ALIGNED16(invstd) && GP_ALIGNED16(gamma),
+                 "gp_bn_bwd: pointers must be 16-byte aligned");
+    if (max_n == 0) return GP_OK;
+    GP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), stream));
+    int rows_per_block = 512;
+    k_bn_bwd_reduce<<<gp_cdiv(max_n, rows_per_block), 256, 2 * C * sizeof(double), stream>>>(
+        dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, sums, rows_per_block);
+    k_bn_bwd_apply<<<ew_grid((long long)max_n * (C / 4)), 256, 0, stream>>>(
+        dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, sums, dY, lddy, dRes, ldres,
+        res_accumulate, dgamma, dbeta);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
+// out[i, :] = F[idx[i], :]  (idx < 0 -> zeros)
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ F, int ldf, int C,
+                                                     const int* __restrict__ idx, int N,
+                                                     float* __restrict__ Out, int ldo) {
+    int cpr = C >> 2;
+    long long total = (long long)N * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / cpr), cg = (int)(t - (long long)i * cpr);
+        int r = __ldg(idx + i);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r >= 0) v = ldg4(F + (size_t)r * ldf + cg * 4);
+        *reinterpret_cast<float4*>(Out + (size_t)i * ldo + cg * 4) = v;
+    }
+}
+
+// dF[idx[i], :] += dOut[i, :]
+__global__ void __launch_bounds__(256) k_scatter_add_rows(const float* __restrict__ dOut, int ldo,
+                                                          int C, const int* __restrict__ idx, int N,
+                                                          float* __restrict__ dF, int ldf) {
+    long long total = (long long)N * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / C), c = (int)(t - (long long)i * C);
+        int r = __ldg(idx + i);
+        if (r >= 0) atomicAdd(dF + (size_t)r * ldf + c, __ldg(dOut + (size_t)i * ldo + c));
+    }
+}
+
+extern "C" int gp_gather_rows(const float* F, int ldf, int C, const int* idx, int N, float* Out,
+                              int ldo, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(C > 0 && C % 4 == 0 && ldf % 4 == 0 && ldo % 4 == 0, "gp_gather_rows: C %% 4 != 0");
+    GP_CHECK_ARG(GP_ALIGNED16(F) && GP_ALIGNED16(Out), "gp_gather_rows: pointers must be 16-byte aligned");
+    if (N == 0) return GP_OK;
+    k_gather_rows<<<ew_grid((long long)N * (C / 4)), 256, 0, stream>>>(F, ldf, C, idx, N, Out, ldo);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
+extern "C" int gp_scatter_add_rows(const float* dOut, int ldo, int C, const int* idx, int N, float* dF,
+                                   int ldf, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(C > 0, "gp_scatter_add_rows: C <= 0");
+    if (N == 0) return GP_OK;
+    k_scatter_add_rows<<<ew_grid((long long)N * C), 256, 0, stream>>>(dOut, ldo, C, idx, N, dF, ldf);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}

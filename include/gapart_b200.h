@@ -1,0 +1,138 @@
+/*
+ * gapart_b200.h - C ABI of libgapart_b200.so, the sm_100a engine behind GAPartNet's
+ * spconv / epic_ops / pointnet2 operator surface.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer into memory owned by the caller (torch tensors);
+ *     the library never allocates, frees or retains pointers beyond the call;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), mirroring
+ *     at::cuda::getCurrentCUDAStream() in the reference's own wrappers
+ *     (dataset/process_tools/utils/pointnet_lib/src/ball_query.cpp:22);
+ *   - return value 0 = ok, negative = error (gp_last_error() holds the text); the library never
+ *     calls exit() (the reference does: ball_query_gpu.cu:62-66) and never throws;
+ *   - data-dependent row counts stay on the device: `d_n` arguments are device int* (may be NULL,
+ *     then the host bound `max_*` is the count) so voxelize -> rulebook -> conv needs no host sync;
+ *   - feature matrices are row-major fp32 [rows, C] with an explicit row stride `ld*` (floats);
+ *   - coordinates are int32 [rows, 4] = (batch, x, y, z), the layout GAPartNet hands to
+ *     spconv.SparseConvTensor (gapartnet/structure/point_cloud.py:139-162).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to /root/reference).
+ */
+#ifndef GAPART_B200_H
+#define GAPART_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+int gp_version(void);
+const char* gp_last_error(void);
+int gp_device_sms(void);
+int gp_fill_i32(int* p, long long n, int value, void* stream);
+int gp_memset(void* p, int byte, long long nbytes, void* stream);
+
+/* ---- occupancy directory ("bitmap-rank perfect hash") ------------------------------------ */
+/* number of uint32 bitmap words for a batch x X x Y x Z grid (-1 if >= 2^32 cells);
+ * prefix needs n_words + 1 ints, scan_tmp needs gp_grid_scan_tmp_ints(n_words) ints. */
+long long gp_grid_num_words(int batch, int X, int Y, int Z);
+long long gp_grid_scan_tmp_ints(long long n_words);
+
+/* Build the directory of an existing coordinate list in arbitrary row order
+ * (spconv.SparseConvTensor(features, indices, spatial_shape, batch_size),
+ *  gapartnet/structure/point_cloud.py:158-162, gapartnet/network/model.py:323-327).
+ * row_of_rank[M] (optional) maps lexicographic rank -> caller row. d_err (optional) gets
+ * bit0 = coordinate out of range, bit1 = duplicate coordinate. */
+int gp_grid_from_coords(const int* coords4, const int* d_n, int max_rows, int batch, int X, int Y,
+                        int Z, uint32_t* words, int* prefix, int* scan_tmp, int* row_of_rank,
+                        int* d_err, void* stream);
+
+/* ---- voxelize ------------------------------------------------------------------------------ */
+/* Per-scene bounding box -/+ pad: apply_voxelization's points_range_min/max
+ * (gapartnet/dataset/gapartnet.py:186-187). range_min/max: [batch, 3]. */
+int gp_scene_range(const float* xyz, int xyz_stride, const int64_t* batch_offsets, int batch,
+                   float pad, float* range_min, float* range_max, void* stream);
+
+/* epic_ops.voxelize.voxelize(points, pt_features, batch_offsets, voxel_size, points_range_min,
+ * points_range_max, reduction="mean") -> (voxel_features, voxel_coords, voxel_batch_indices,
+ * pc_voxel_id)   (gapartnet/dataset/gapartnet.py:188-195, network/grouping_utils.py:93-101).
+ * voxel id = floor((p - range_min) / voxel_size) per axis; a point is kept iff
+ * range_min <= p < range_max and its voxel id < (X,Y,Z); rows come out in lexicographic
+ * (batch,x,y,z) order; voxel_coords4 = [M,4] (b,x,y,z); pc_voxel_id[i] = row or -1.
+ * voxel_size/range_*: device float[3] (range_per_scene=1: [batch,3]).
+ * Workspaces: words[n_words], prefix[n_words+1], scan_tmp, pt_cell[N], voxel_cnt[max_voxels].
+ * Outputs beyond max_voxels are dropped (d_num_voxels still reports the true count). */
+int gp_voxelize(const float* xyz, int xyz_stride, const float* feats, int C, int feat_stride,
+                const int64_t* batch_offsets, int batch, int N, const float* voxel_size,
+                const float* range_min, const float* range_max, int range_per_scene, int X, int Y,
+                int Z, uint32_t* words, int* prefix, int* scan_tmp, uint32_t* pt_cell,
+                int max_voxels, float* voxel_feats, int* voxel_cnt, int* voxel_coords4,
+                int* pc_voxel_id, int* d_num_voxels, int* d_batch_splits, void* stream);
+
+/* ---- rulebooks (indice pairs) ---------------------------------------------------------------- */
+/* SubMConv3d(kernel_size=3, padding=1, indice_key=...) pair table
+ * (gapartnet/network/backbone.py:25-28,33-36,149-152):
+ * nbr[k*tbl_stride + i] = row at coord(i) + (k0-1,k1-1,k2-1), k = k0*9+k1*3+k2, or -1. */
+int gp_rulebook_subm3(const int* coords4, const int* d_n, int max_rows, int batch, int X, int Y, int Z,
+                      const uint32_t* words, const int* prefix, const int* row_of_rank, int* nbr,
+                      int tbl_stride, void* stream);
+
+/* SparseConv3d(kernel_size=2, stride=2, indice_key="spconv{i}") and its SparseInverseConv3d twin
+ * (gapartnet/network/backbone.py:74-77,87-90). Builds the child level (dims X/2,Y/2,Z/2, rows in
+ * lexicographic order) and two views of the pair list, tap k = (x&1)*4+(y&1)*2+(z&1):
+ *   child [k*child_stride  + o] = input row feeding output row o through tap k, or -1
+ *   parent8[k*parent_stride + i] = output row fed by input row i if its tap is k, else -1 */
+int gp_rulebook_down2(const int* coords4_in, const int* d_n_in, int max_in, int batch, int X, int Y,
+                      int Z, uint32_t* words_out, int* prefix_out, int* scan_tmp, int max_out,
+                      int* coords4_out, int* d_n_out, int* child, int child_stride, int* parent8,
+                      int parent_stride, void* stream);
+
+/* ---- sparse convolution (output stationary gather-GEMM) -------------------------------------- */
+/* Y[i, co] (+)= sum_k sum_ci X[nbr[k][i], ci] * W(k', ci, co), k' = flip_k ? K-1-k : k,
+ * W(k,ci,co) = W[k*w_sk + ci*w_sci + co*w_sco]. nbr == NULL (K must be 1) = identity (k1 conv).
+ * Serves spconv.SubMConv3d / SparseConv3d / SparseInverseConv3d forward and, with swapped
+ * channel strides (+flip_k for SubM), their input gradients.
+ * stats (optional): double[2*Cout], += per-channel sum and sum of squares of Y (BatchNorm1d). */
+int gp_conv_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
+                long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K,
+                const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
+                double* stats, void* stream);
+
+/* dW(k', ci, co) += sum_i X[nbr[k][i], ci] * dY[i, co] */
+int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout,
+                  const int* nbr, int tbl_stride, int K, const int* d_n_out, int max_out, float* dW,
+                  long long w_sk, long long w_sci, long long w_sco, int flip_k, void* stream);
+
+/* ---- BatchNorm1d(eps=1e-4, momentum=0.1) in training mode + ReLU + residual ------------------- */
+/* (norm_fn gapartnet/network/model.py:86; ResBlock.forward gapartnet/network/backbone.py:40-49) */
+int gp_col_stats(const float* Y, int ldy, int C, const int* d_n, int max_n, double* stats,
+                 void* stream);
+int gp_bn_finalize(const double* stats, int C, const int* d_n, int max_n, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean,
+                   float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                   void* stream);
+/* Out = [relu](Y*scale + shift [+ residual]) */
+int gp_bn_apply(const float* Y, int ldy, int C, const int* d_n, int max_n, const float* scale,
+                const float* shift, const float* residual, int ldr, int relu, float* Out, int ldo,
+                void* stream);
+/* dz = dA * (A > 0) (A == NULL: no ReLU); dY = BN backward of dz; dRes (optional) (+)= dz;
+ * dgamma/dbeta (optional) += ; sums: double[2C] scratch. */
+int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const float* Y, int ldy, int C,
+              const int* d_n, int max_n, const float* mean, const float* invstd, const float* gamma,
+              double* sums, float* dY, int lddy, float* dRes, int ldres, int res_accumulate,
+              float* dgamma, float* dbeta, void* stream);
+
+/* ---- voxel <-> point rows (pc_feature = features[pc_voxel_id], network/model.py:153,359,394) -- */
+int gp_gather_rows(const float* F, int ldf, int C, const int* idx, int N, float* Out, int ldo,
+                   void* stream);
+int gp_scatter_add_rows(const float* dOut, int ldo, int C, const int* idx, int N, float* dF, int ldf,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAPART_B200_H */
