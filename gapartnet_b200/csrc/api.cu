@@ -32,6 +32,11 @@ int gp_num_sms() {
 
 extern "C" int gp_device_sms(void) { return gp_num_sms(); }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void gp_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long gp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 // fill an int32 / fp32 buffer (stream ordered); avoids a torch op inside graph-captured plans
 __global__ void k_fill_i32(int* p, long long n, int v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -43,6 +48,7 @@ extern "C" int gp_fill_i32(int* p, long long n, int v, void* stream_) {
     long long b = (n + 255) / 256;
     if (b > 4096) b = 4096;
     k_fill_i32<<<(int)b, 256, 0, (cudaStream_t)stream_>>>(p, n, v);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }

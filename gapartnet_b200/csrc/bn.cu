@@ -13,14 +13,20 @@ __global__ void k_bn_finalize(const double* __restrict__ stats, int C, const int
                               int max_n, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float eps, float momentum,
                               float* __restrict__ running_mean, float* __restrict__ running_var,
-                              float* __restrict__ scale, float* __restrict__ shift,
+                              int use_running, float* __restrict__ scale, float* __restrict__ shift,
                               float* __restrict__ mean_o, float* __restrict__ invstd_o) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     int n = gp_rows(d_n, max_n);
     double cnt = n > 0 ? (double)n : 1.0;
-    double mean = stats[c] / cnt;
-    double var = stats[C + c] / cnt - mean * mean;
+    double mean, var;
+    if (use_running) {  // eval mode: normalise with the running statistics, do not update them
+        mean = running_mean[c];
+        var = running_var[c];
+    } else {
+        mean = stats[c] / cnt;
+        var = stats[C + c] / cnt - mean * mean;
+    }
     if (var < 0.0) var = 0.0;
     float invstd = (float)(1.0 / sqrt(var + (double)eps));
     float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
@@ -29,7 +35,7 @@ __global__ void k_bn_finalize(const double* __restrict__ stats, int C, const int
     shift[c] = b - (float)mean * sc;
     mean_o[c] = (float)mean;
     invstd_o[c] = invstd;
-    if (running_mean && n > 0) {
+    if (running_mean && !use_running && n > 0) {
         double unbiased = n > 1 ? var * cnt / (cnt - 1.0) : var;
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
@@ -38,13 +44,15 @@ __global__ void k_bn_finalize(const double* __restrict__ stats, int C, const int
 
 extern "C" int gp_bn_finalize(const double* stats, int C, const int* d_n, int max_n,
                               const float* gamma, const float* beta, float eps, float momentum,
-                              float* running_mean, float* running_var, float* scale, float* shift,
-                              float* mean, float* invstd, void* stream_) {
+                              float* running_mean, float* running_var, int use_running,
+                              float* scale, float* shift, float* mean, float* invstd, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(C > 0, "gp_bn_finalize: C <= 0");
+    GP_CHECK_ARG(!use_running || (running_mean && running_var), "gp_bn_finalize: eval mode needs running stats");
     k_bn_finalize<<<gp_cdiv(C, 128), 128, 0, stream>>>(stats, C, d_n, max_n, gamma, beta, eps, momentum,
-                                                       running_mean, running_var, scale, shift, mean,
-                                                       invstd);
+                                                       running_mean, running_var, use_running, scale,
+                                                       shift, mean, invstd);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -89,6 +97,7 @@ extern "C" int gp_col_stats(const float* Y, int ldy, int C, const int* d_n, int 
     int rows_per_block = 512;
     k_col_stats<<<gp_cdiv(max_n, rows_per_block), 256, 2 * C * sizeof(double), stream>>>(
         Y, ldy, C, d_n, max_n, stats, rows_per_block);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -143,6 +152,7 @@ extern "C" int gp_bn_apply(const float* Y, int ldy, int C, const int* d_n, int m
     k_bn_apply<<<ew_grid((long long)max_n * (C / 4)), 256, 0, stream>>>(Y, ldy, C, d_n, max_n, scale,
                                                                         shift, residual, ldr, relu, Out,
                                                                         ldo);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(
 extern "C" int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const float* Y, int ldy,
                          int C, const int* d_n, int max_n, const float* mean, const float* invstd,
                          const float* gamma, double* sums, float* dY, int lddy, float* dRes, int ldres,
-                         int res_accumulate, float* dgamma, float* dbeta, void* stream_) {
+                         int res_accumulate, float* dgamma, float* dbeta, int zero_sums, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024, "gp_bn_bwd: C must be a multiple of 4");
     GP_CHECK_ARG(lda % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && (!A || la % 4 == 0) &&
@@ -261,13 +271,14 @@ extern "C" int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const
                      GP_ALIGNED16(dRes) && GP_ALIGNED16(mean) && GP_ALIGNED16(invstd) && GP_ALIGNED16(gamma),
                  "gp_bn_bwd: pointers must be 16-byte aligned");
     if (max_n == 0) return GP_OK;
-    GP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), stream));
+    if (zero_sums) GP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), stream));
     int rows_per_block = 512;
     k_bn_bwd_reduce<<<gp_cdiv(max_n, rows_per_block), 256, 2 * C * sizeof(double), stream>>>(
         dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, sums, rows_per_block);
     k_bn_bwd_apply<<<ew_grid((long long)max_n * (C / 4)), 256, 0, stream>>>(
         dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, sums, dY, lddy, dRes, ldres,
         res_accumulate, dgamma, dbeta);
+    gp_note_launch(2);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -308,6 +319,7 @@ extern "C" int gp_gather_rows(const float* F, int ldf, int C, const int* idx, in
     GP_CHECK_ARG(GP_ALIGNED16(F) && GP_ALIGNED16(Out), "gp_gather_rows: pointers must be 16-byte aligned");
     if (N == 0) return GP_OK;
     k_gather_rows<<<ew_grid((long long)N * (C / 4)), 256, 0, stream>>>(F, ldf, C, idx, N, Out, ldo);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -318,6 +330,7 @@ extern "C" int gp_scatter_add_rows(const float* dOut, int ldo, int C, const int*
     GP_CHECK_ARG(C > 0, "gp_scatter_add_rows: C <= 0");
     if (N == 0) return GP_OK;
     k_scatter_add_rows<<<ew_grid((long long)N * C), 256, 0, stream>>>(dOut, ldo, C, idx, N, dF, ldf);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }

@@ -44,6 +44,9 @@ void gp_set_error(const char* fmt, ...);
 
 static inline int gp_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// kernel-launch accounting (bench.py reports gpu_launches from it)
+void gp_note_launch(int n);
+
 // number of SMs of the current device (cached); B200 = 148
 int gp_num_sms();
 

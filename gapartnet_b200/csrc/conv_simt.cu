@@ -161,6 +161,7 @@ extern "C" int gp_conv_fwd(const float* X, int ldx, int Cin, const float* W, lon
                                                               flip_k, nbr, tbl_stride, K, d_n_out,
                                                               max_out, Y, ldy, Cout, accumulate, stats);
     }
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -259,6 +260,7 @@ extern "C" int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, 
     dim3 grid(chunks, K, zt);
     k_conv_wgrad<<<grid, 256, 0, stream>>>(X, ldx, Cin, dY, ldy, Cout, nbr, tbl_stride, K, d_n_out,
                                            max_out, dW, w_sk, w_sci, w_sco, flip_k, rows_per_block);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }

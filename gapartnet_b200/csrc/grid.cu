@@ -114,6 +114,7 @@ int gp_grid_scan(const uint32_t* words, long long n_words, int* prefix, int* sca
     k_scan_block_sums<<<nb, SCAN_THREADS, 0, stream>>>(words, n_words, scan_tmp);
     k_scan_block_offsets<<<1, 1024, 0, stream>>>(scan_tmp, nb, prefix + n_words, d_total);
     k_scan_write<<<nb, SCAN_THREADS, 0, stream>>>(words, n_words, scan_tmp, prefix);
+    gp_note_launch(3);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -274,6 +275,7 @@ extern "C" int gp_scene_range(const float* xyz, int xyz_stride, const int64_t* b
     GP_CHECK_ARG(batch > 0 && xyz_stride >= 3, "gp_scene_range: bad batch/stride");
     k_scene_range<<<batch, 256, 0, stream>>>(xyz, xyz_stride, (const long long*)batch_offsets, pad,
                                              range_min, range_max);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -307,12 +309,14 @@ extern "C" int gp_voxelize(const float* xyz, int xyz_stride, const float* feats,
         k_vox_mark<<<gp_cdiv(N, 256), 256, 0, stream>>>(
             xyz, xyz_stride, (const long long*)batch_offsets, batch, N, voxel_size, range_min,
             range_max, range_per_scene ? 3 : 0, X, Y, Z, ss, words, pt_cell);
+        gp_note_launch(1);
     }
     int rc = gp_grid_scan(words, n_words, prefix, scan_tmp, d_num_voxels, stream);
     if (rc) return rc;
     k_grid_emit<<<gp_cdiv(n_words, 256), 256, 0, stream>>>(words, prefix, n_words, max_voxels, ss, Y,
                                                            Z, batch, (int4*)voxel_coords4,
                                                            d_batch_splits);
+    gp_note_launch(1);
     if (N > 0) {
         long long tot = (long long)N * C;
         k_vox_accum<<<gp_cdiv(tot, 256), 256, 0, stream>>>(pt_cell, feats, C, feat_stride, N, words,
@@ -321,6 +325,7 @@ extern "C" int gp_voxelize(const float* xyz, int xyz_stride, const float* feats,
         long long totv = (long long)max_voxels * C;
         k_vox_mean<<<gp_cdiv(totv, 256), 256, 0, stream>>>(voxel_feats, voxel_cnt, C, d_num_voxels,
                                                            max_voxels);
+        gp_note_launch(2);
     }
     GP_LAUNCH_CHECK();
     return GP_OK;
@@ -372,11 +377,13 @@ extern "C" int gp_grid_from_coords(const int* coords4, const int* d_n, int max_r
     if (max_rows > 0)
         k_coords_mark<<<gp_cdiv(max_rows, 256), 256, 0, stream>>>((const int4*)coords4, d_n, max_rows,
                                                                  batch, X, Y, Z, ss, words, d_err);
+    gp_note_launch(max_rows > 0 ? 1 : 0);
     int rc = gp_grid_scan(words, n_words, prefix, scan_tmp, nullptr, stream);
     if (rc) return rc;
     if (row_of_rank && max_rows > 0)
         k_coords_rank<<<gp_cdiv(max_rows, 256), 256, 0, stream>>>(
             (const int4*)coords4, d_n, max_rows, batch, X, Y, Z, ss, words, prefix, row_of_rank);
+    gp_note_launch((row_of_rank && max_rows > 0) ? 1 : 0);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -413,6 +420,7 @@ extern "C" int gp_rulebook_subm3(const int* coords4, const int* d_n, int max_row
     GridDir g{words, prefix, row_of_rank, batch, X, Y, Z, gp_scene_stride(X, Y, Z)};
     k_rulebook_subm3<<<gp_cdiv(max_rows, 256), 256, 0, stream>>>((const int4*)coords4, d_n, max_rows,
                                                                  g, nbr, tbl_stride);
+    gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
@@ -482,6 +490,7 @@ extern "C" int gp_rulebook_down2(const int* coords4_in, const int* d_n_in, int m
         k_down_tables<<<gp_cdiv(max_in, 256), 256, 0, stream>>>(
             (const int4*)coords4_in, d_n_in, max_in, X2, Y2, Z2, ss2, words_out, prefix_out, max_out,
             child, child_stride, parent8, parent_stride);
+    gp_note_launch(max_in > 0 ? 3 : 1);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }

@@ -1,0 +1,442 @@
+"""Fused, sync-free execution plan for a GAPartNet SparseUNet (forward + backward).
+
+The per-op modules in gapartnet_b200.spconv.pytorch follow spconv's API (exact-shaped tensors, one
+host sync per strided conv).  This engine executes the same graph
+(/root/reference/gapartnet/network/backbone.py:8-165, driven by network/model.py:145-158) as a
+static launch sequence over preallocated arenas:
+
+  points [N,6] --voxelize--> level-0 rows --(subm3 / down2 rulebooks per level)-->
+  conv(+BN statistics in the epilogue) -> BN finalize -> BN/ReLU/residual apply ... -> voxel->point
+  gather -> pc_feature [N, C0]
+
+Row counts of every level live on the device, grids are sized from static bounds, and nothing
+allocates or synchronises, so the whole step can be captured in a CUDA graph (no tracing
+compiler).  Channel concatenation (backbone.py:119) is free: producers write straight into column
+slices of the concat buffer via row strides.  Parameters stay in the torch modules (spconv KRSC
+layout, state_dict compatible); gradients are written into a flat arena that DDP-style allreduce
+can consume in one call.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import C, GapartError
+from .ops import _p
+
+
+class _Act:
+    """A [rows, C] fp32 activation living in (a column slice of) an arena buffer."""
+
+    def __init__(self, t: torch.Tensor, level: int):
+        assert t.dim() == 2 and t.stride(1) == 1
+        self.t = t
+        self.level = level
+        self.C = t.shape[1]
+        self.ld = t.stride(0)
+        self.grad: Optional[torch.Tensor] = None   # same shape/stride family as t
+        self.grad_ready = False                     # build-time: has a backward op written it yet?
+        self.needs_grad = True
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+class SparseUNetEngine:
+    """Executes `net` (a SparseUNet built by network.backbone.make_classes(sp) on
+    gapartnet_b200.spconv.pytorch) on batches of up to `max_points` points in `batch` scenes."""
+
+    def __init__(self, net: nn.Module, batch: int, max_points: int, spatial_shape: Sequence[int],
+                 voxel_size: float, in_channels: int, max_rows: Optional[Sequence[int]] = None,
+                 input_needs_grad: bool = False, bn_eps: float = 1e-4, bn_momentum: float = 0.1):
+        p0 = next(net.parameters())
+        if not p0.is_cuda:
+            raise GapartError("SparseUNetEngine needs the module on a CUDA device")
+        self.dev = p0.device
+        self.net = net
+        self.B, self.N = int(batch), int(max_points)
+        self.shape0 = tuple(int(s) for s in spatial_shape)
+        self.voxel_size = float(voxel_size)
+        self.in_channels = in_channels
+        self.eps, self.momentum = float(bn_eps), float(bn_momentum)
+        self.training = True
+        self.input_needs_grad = input_needs_grad
+        self._stream = None
+
+        # ---- level geometry ---------------------------------------------------------------
+        chans = list(net.ublock.channels)
+        ub = net.ublock
+        depth = 1
+        while len(ub.channels) > 1:
+            ub = ub.ublock
+            depth += 1
+        self.depth = depth
+        self.shapes = [self.shape0]
+        for _ in range(depth - 1):
+            s = self.shapes[-1]
+            self.shapes.append((s[0] // 2, s[1] // 2, s[2] // 2))
+        if max_rows is None:
+            max_rows = [self.N]
+        self.max_rows = [int(max_rows[0])]
+        for L in range(1, depth):
+            s = self.shapes[L]
+            bound = min(self.max_rows[L - 1], self.B * s[0] * s[1] * s[2])
+            if len(max_rows) > L:
+                bound = min(bound, int(max_rows[L]))
+            self.max_rows.append(max(bound, 1))
+
+        dev = self.dev
+        i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        # ---- level state --------------------------------------------------------------------
+        self.coords = [i32(m, 4) for m in self.max_rows]
+        self.d_n = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in self.max_rows]
+        self.grids = [ops.GridDir.alloc(self.B, s, dev) for s in self.shapes]
+        self.scan_tmp = [g.scan_tmp() for g in self.grids]
+        self.nbr = [i32(27, m) for m in self.max_rows]
+        self.child = [i32(8, self.max_rows[L + 1]) for L in range(depth - 1)]
+        self.parent8 = [i32(8, self.max_rows[L]) for L in range(depth - 1)]
+        # voxelize workspaces
+        self.vox_feats = f32(self.max_rows[0], in_channels)
+        self.vox_cnt = i32(self.max_rows[0])
+        self.pt_cell = i32(self.N)
+        self.pc_voxel_id = i32(self.N)
+        self.batch_splits = i32(self.B + 1)
+        self.rmin = f32(self.B, 3)
+        self.rmax = f32(self.B, 3)
+        self.vs = torch.full((3,), self.voxel_size, dtype=torch.float32, device=dev)
+        # static inputs
+        self.points = f32(self.N, in_channels)
+        self.batch_offsets = torch.zeros(self.B + 1, dtype=torch.int64, device=dev)
+
+        # ---- program ----------------------------------------------------------------------------
+        self._fwd: List[Callable[[], None]] = []
+        self._bwd_units: List[Callable[[], None]] = []   # in forward order; executed reversed
+        self._stats_chunks: List[torch.Tensor] = []
+        self._n_launch_fwd = 0
+        self._n_launch_bwd = 0
+        self._dy_pool: Dict[Tuple[int, int], _Act] = {}
+        self._cur_stream = None
+        self._stat_arena = None
+        self._stat_used = 0
+        self._keep: List[torch.Tensor] = []
+        self._build()
+
+    # ------------------------------------------------------------------------------------------
+    def _new_act(self, level: int, C_: int, into: Optional[torch.Tensor] = None) -> _Act:
+        t = into if into is not None else torch.empty(self.max_rows[level], C_, dtype=torch.float32,
+                                                      device=self.dev)
+        self._keep.append(t)
+        return _Act(t, level)
+
+    def _grad_of(self, a: _Act) -> torch.Tensor:
+        if a.grad is None:
+            a.grad = torch.zeros(self.max_rows[a.level], a.C, dtype=torch.float32, device=self.dev)
+        self._keep.append(a.grad)
+        return a.grad
+
+    def _s(self):
+        return self._cur_stream
+
+    def _bind_stream(self):
+        self._cur_stream = torch.cuda.current_stream().cuda_stream
+        return self._cur_stream
+
+    def _dy_scratch(self, level: int, C_: int) -> _Act:
+        key = (level, C_)
+        if key not in self._dy_pool:
+            self._dy_pool[key] = self._new_act(level, C_)
+        return self._dy_pool[key]
+
+    def _bn_buffers(self, C_: int):
+        """carve (forward stats, backward sums) from one fp64 arena that a single memset clears"""
+        if self._stat_arena is None:
+            self._stat_arena = torch.zeros(1 << 17, dtype=torch.float64, device=self.dev)
+            self._stat_used = 0
+        o = self._stat_used
+        if o + 4 * C_ > self._stat_arena.numel():
+            raise GapartError("BN statistics arena exhausted")
+        stats = self._stat_arena[o:o + 2 * C_]
+        sums = self._stat_arena[o + 2 * C_:o + 4 * C_]
+        self._stat_used = o + 4 * C_
+        vec = torch.empty(4, C_, dtype=torch.float32, device=self.dev)  # scale, shift, mean, invstd
+        self._keep.append(vec)  # closures hold raw pointers: the engine owns every buffer
+        return stats, sums, vec
+
+    # conv + BN (+ReLU) (+residual) unit ---------------------------------------------------------
+    def _unit_conv_bn(self, x: _Act, conv: nn.Module, bn: nn.BatchNorm1d, out_level: int, kind: str,
+                      relu: bool, residual: Optional[_Act] = None, into: Optional[torch.Tensor] = None) -> _Act:
+        """kind: 'subm3' | 'k1' | 'down' (x.level -> x.level+1) | 'up' (x.level -> x.level-1)"""
+        Lx, Lo = x.level, out_level
+        w = conv.weight
+        Cout, Cin = w.shape[0], w.shape[-1]
+        assert Cin == x.C, (Cin, x.C)
+        if kind == "subm3":
+            K, tbl_f, tbl_b, flip_b = 27, self.nbr[Lx], self.nbr[Lx], 1
+        elif kind == "k1":
+            K, tbl_f, tbl_b, flip_b = 1, None, None, 0
+        elif kind == "down":
+            K, tbl_f, tbl_b, flip_b = 8, self.child[Lx], self.parent8[Lx], 0
+        elif kind == "up":
+            K, tbl_f, tbl_b, flip_b = 8, self.parent8[Lo], self.child[Lo], 0
+        else:
+            raise ValueError(kind)
+        n_out, d_n_out = self.max_rows[Lo], self.d_n[Lo]
+        n_in, d_n_in = self.max_rows[Lx], self.d_n[Lx]
+        y = self._new_act(Lo, Cout)
+        a = self._new_act(Lo, Cout, into)
+        stats, sums, vec = self._bn_buffers(Cout)
+        tsf = tbl_f.shape[1] if tbl_f is not None else 0
+        tsb = tbl_b.shape[1] if tbl_b is not None else 0
+        wp = w.data_ptr()
+        g_ptr, b_ptr = bn.weight.data_ptr(), bn.bias.data_ptr()
+        rm_ptr, rv_ptr = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        sc, sh, mu, istd = (vec[i].data_ptr() for i in range(4))
+        res_ptr, res_ld = (residual.ptr, residual.ld) if residual is not None else (None, 0)
+        eng = self
+
+        def fwd():
+            s = eng._s()
+            C.gp_conv_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
+                          y.ptr, y.ld, Cout, 0, _p(stats) if eng.training else None, s)
+            C.gp_bn_finalize(_p(stats), Cout, _p(d_n_out), n_out, g_ptr, b_ptr, eng.eps, eng.momentum,
+                             rm_ptr, rv_ptr, 0 if eng.training else 1, sc, sh, mu, istd, s)
+            C.gp_bn_apply(y.ptr, y.ld, Cout, _p(d_n_out), n_out, sc, sh, res_ptr, res_ld, int(relu),
+                          a.ptr, a.ld, s)
+
+        self._fwd.append(fwd)
+        self._n_launch_fwd += 3
+
+        def make_bwd():
+            # called during the reverse build pass so that first-writer flags follow execution order
+            da = eng._grad_of(a)
+            # dY is consumed at once by this unit's dgrad + wgrad: one scratch per (level, C)
+            dy = eng._dy_scratch(Lo, Cout)
+            dres_ptr, dres_ld, dres_acc = None, 0, 0
+            if residual is not None and residual.needs_grad:
+                rg = eng._grad_of(residual)
+                dres_ptr, dres_ld, dres_acc = rg.data_ptr(), rg.stride(0), int(residual.grad_ready)
+                residual.grad_ready = True
+            dx_ptr = dx_ld = None
+            dx_acc = 0
+            if x.needs_grad:
+                xg = eng._grad_of(x)
+                dx_ptr, dx_ld, dx_acc = xg.data_ptr(), xg.stride(0), int(x.grad_ready)
+                x.grad_ready = True
+            wg = conv.weight.grad
+            gg, bg = bn.weight.grad, bn.bias.grad
+            wg_ptr, gg_ptr, bg_ptr = wg.data_ptr(), gg.data_ptr(), bg.data_ptr()
+            a_ptr = a.ptr if relu else None
+            n_launch = 3 + (1 if dx_ptr is not None else 0)
+
+            def bwd():
+                s = eng._s()
+                C.gp_bn_bwd(da.data_ptr(), da.stride(0), a_ptr, a.ld, y.ptr, y.ld, Cout, _p(d_n_out), n_out,
+                            mu, istd, g_ptr, _p(sums), dy.ptr, dy.ld, dres_ptr, dres_ld, dres_acc,
+                            gg_ptr, bg_ptr, 0, s)
+                if dx_ptr is not None:
+                    C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
+                                  _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
+                C.gp_conv_wgrad(x.ptr, x.ld, Cin, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
+                                wg_ptr, Cin, 1, K * Cin, 0, s)
+
+            return bwd, n_launch
+
+        self._bwd_units.append(make_bwd)
+        return a
+
+    # BN + ReLU on an existing activation (the `without_stem` stem, backbone.py:157-160) -----------
+    def _unit_bn_only(self, x: _Act, bn: nn.BatchNorm1d, relu: bool) -> _Act:
+        L, Cc = x.level, x.C
+        n, d_n = self.max_rows[L], self.d_n[L]
+        a = self._new_act(L, Cc)
+        stats, sums, vec = self._bn_buffers(Cc)
+        g_ptr, b_ptr = bn.weight.data_ptr(), bn.bias.data_ptr()
+        rm_ptr, rv_ptr = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        sc, sh, mu, istd = (vec[i].data_ptr() for i in range(4))
+        eng = self
+
+        def fwd():
+            s = eng._s()
+            if eng.training:
+                C.gp_col_stats(x.ptr, x.ld, Cc, _p(d_n), n, _p(stats), s)
+            C.gp_bn_finalize(_p(stats), Cc, _p(d_n), n, g_ptr, b_ptr, eng.eps, eng.momentum, rm_ptr, rv_ptr,
+                             0 if eng.training else 1, sc, sh, mu, istd, s)
+            C.gp_bn_apply(x.ptr, x.ld, Cc, _p(d_n), n, sc, sh, None, 0, int(relu), a.ptr, a.ld, s)
+
+        self._fwd.append(fwd)
+        self._n_launch_fwd += 3
+
+        def make_bwd():
+            da = eng._grad_of(a)
+            gg_ptr, bg_ptr = bn.weight.grad.data_ptr(), bn.bias.grad.data_ptr()
+            a_ptr = a.ptr if relu else None
+            if x.needs_grad:
+                assert not x.grad_ready, "bn-only stem must be the first writer of its input gradient"
+                xg = eng._grad_of(x)
+                x.grad_ready = True
+                dst, dst_ld = xg.data_ptr(), xg.stride(0)
+            else:  # still need dgamma/dbeta: write dY into a scratch
+                scratch = torch.empty_like(a.t)
+                eng._keep.append(scratch)
+                dst, dst_ld = scratch.data_ptr(), scratch.stride(0)
+
+            def bwd():
+                C.gp_bn_bwd(da.data_ptr(), da.stride(0), a_ptr, a.ld, x.ptr, x.ld, Cc, _p(d_n), n, mu, istd,
+                            g_ptr, _p(sums), dst, dst_ld, None, 0, 0, gg_ptr, bg_ptr, 0, eng._s())
+
+            return bwd, 2
+
+        self._bwd_units.append(make_bwd)
+        return a
+
+    # graph walkers ------------------------------------------------------------------------------
+    def _res_block(self, blk: nn.Module, x: _Act, into: Optional[torch.Tensor] = None) -> _Act:
+        L = x.level
+        if isinstance(blk.shortcut, nn.Identity):
+            skip = x
+        else:
+            skip = self._unit_conv_bn(x, blk.shortcut[0], blk.shortcut[1], L, "k1", relu=False)
+        h = self._unit_conv_bn(x, blk.conv1[0], blk.conv1[1], L, "subm3", relu=True)
+        return self._unit_conv_bn(h, blk.conv2[0], blk.conv2[1], L, "subm3", relu=True, residual=skip, into=into)
+
+    def _ublock(self, ub: nn.Module, x: _Act) -> _Act:
+        L = x.level
+        blocks = list(ub.encoder_blocks._modules.values())
+        has_child = len(ub.channels) > 1
+        c0 = ub.channels[0]
+        cat = None
+        if has_child:
+            cat = torch.empty(self.max_rows[L], 2 * c0, dtype=torch.float32, device=self.dev)
+        for i, blk in enumerate(blocks):
+            last = i == len(blocks) - 1
+            x = self._res_block(blk, x, into=cat[:, c0:] if (last and has_child) else None)
+        if not has_child:
+            return x
+        skip = x
+        d = self._unit_conv_bn(skip, ub.downsample[0], ub.downsample[1], L + 1, "down", relu=True)
+        d = self._ublock(ub.ublock, d)
+        up = self._unit_conv_bn(d, ub.upsample[0], ub.upsample[1], L, "up", relu=True, into=cat[:, :c0])
+        # concat([up, skip]) (backbone.py:119) is the buffer itself; its gradient is shared too
+        catg = torch.zeros(self.max_rows[L], 2 * c0, dtype=torch.float32, device=self.dev)
+        up.grad, skip.grad = catg[:, :c0], catg[:, c0:]
+        # the decoder (first in backward order) writes the whole concat gradient
+        up.grad_ready = skip.grad_ready = True
+        y = _Act(cat, L)
+        y.grad = catg
+        for blk in ub.decoder_blocks._modules.values():
+            y = self._res_block(blk, y)
+        return y
+
+    def _build(self):
+        net = self.net
+        # one flat fp32 gradient arena (DDP-style: a single allreduce covers every parameter)
+        params = list(net.parameters())
+        total = sum(p.numel() for p in params)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        off = 0
+        for p in params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        x0 = _Act(self.vox_feats, 0)
+        x0.needs_grad = self.input_needs_grad
+        stem = list(net.stem._modules.values()) if net.stem is not None else []
+        if stem and not isinstance(stem[0], nn.BatchNorm1d):
+            x = self._unit_conv_bn(x0, stem[0], stem[1], 0, "subm3", relu=True)
+        elif stem:
+            x = self._unit_bn_only(x0, stem[0], relu=True)
+        else:
+            x = x0
+        out = self._ublock(net.ublock, x)
+        self.out_act = out
+        self.x0 = x0
+        self.out_grad = self._grad_of(out)
+        out.grad_ready = True
+        self.pc_feature = torch.empty(self.N, out.C, dtype=torch.float32, device=self.dev)
+        self.d_pc_feature = torch.zeros(self.N, out.C, dtype=torch.float32, device=self.dev)
+        # reverse pass: instantiate backward closures in execution order
+        self._bwd = []
+        for mk in reversed(self._bwd_units):
+            fn, nl = mk()
+            self._bwd.append(fn)
+            self._n_launch_bwd += nl
+
+    # ------------------------------------------------------------------------------------------
+    def build_levels(self):
+        """voxelize (points -> level 0) + every rulebook of the step; no host sync."""
+        s = self._bind_stream()
+        N, B = self.N, self.B
+        C.gp_scene_range(_p(self.points), self.points.stride(0), _p(self.batch_offsets), B, 1e-4,
+                         _p(self.rmin), _p(self.rmax), s)
+        g0 = self.grids[0]
+        C.gp_voxelize(_p(self.points), self.points.stride(0), _p(self.points), self.in_channels,
+                      self.points.stride(0), _p(self.batch_offsets), B, N, _p(self.vs), _p(self.rmin),
+                      _p(self.rmax), 1, *g0.shape, _p(g0.words), _p(g0.prefix), _p(self.scan_tmp[0]),
+                      _p(self.pt_cell), self.max_rows[0], _p(self.vox_feats), _p(self.vox_cnt),
+                      _p(self.coords[0]), _p(self.pc_voxel_id), _p(self.d_n[0]), _p(self.batch_splits), s)
+        self._rulebooks(s)
+
+    def _rulebooks(self, s):
+        B = self.B
+        for L in range(self.depth):
+            g = self.grids[L]
+            C.gp_rulebook_subm3(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], B, *g.shape,
+                                _p(g.words), _p(g.prefix), _p(g.row_of_rank), _p(self.nbr[L]),
+                                self.nbr[L].shape[1], s)
+            if L + 1 < self.depth:
+                g2 = self.grids[L + 1]
+                C.gp_rulebook_down2(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], B, *g.shape,
+                                    _p(g2.words), _p(g2.prefix), _p(self.scan_tmp[L + 1]),
+                                    self.max_rows[L + 1], _p(self.coords[L + 1]), _p(self.d_n[L + 1]),
+                                    _p(self.child[L]), self.child[L].shape[1], _p(self.parent8[L]),
+                                    self.parent8[L].shape[1], s)
+
+    def run_forward(self):
+        """levels must be built; -> self.pc_feature [N, C0] (static buffer)."""
+        s = self._bind_stream()
+        if self._stat_used:
+            C.gp_memset(_p(self._stat_arena), 0, self._stat_used * 8, s)
+        for op in self._fwd:
+            op()
+        o = self.out_act
+        C.gp_gather_rows(o.ptr, o.ld, o.C, _p(self.pc_voxel_id), self.N, _p(self.pc_feature),
+                         self.pc_feature.stride(0), s)
+        return self.pc_feature
+
+    def run_backward(self):
+        """consumes self.d_pc_feature [N, C0]; accumulates into every parameter's .grad."""
+        s = self._bind_stream()
+        og = self.out_grad
+        C.gp_memset(_p(og), 0, og.numel() * 4, s)
+        C.gp_scatter_add_rows(_p(self.d_pc_feature), self.d_pc_feature.stride(0), og.shape[1],
+                              _p(self.pc_voxel_id), self.N, _p(og), og.stride(0), s)
+        for op in self._bwd:
+            op()
+
+    # convenience --------------------------------------------------------------------------------
+    def load_points(self, points: torch.Tensor, batch_offsets: torch.Tensor):
+        assert points.shape == self.points.shape, (points.shape, self.points.shape)
+        self.points.copy_(points, non_blocking=True)
+        self.batch_offsets.copy_(batch_offsets, non_blocking=True)
+
+    def forward_points(self, points: torch.Tensor, batch_offsets: torch.Tensor) -> torch.Tensor:
+        self.load_points(points, batch_offsets)
+        self.build_levels()
+        return self.run_forward()
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def level_counts(self) -> List[int]:
+        """host copy of the per-level row counts (syncs; diagnostics only)."""
+        return [int(d.item()) for d in self.d_n]
+
+    @property
+    def launches_per_step(self) -> int:
+        # voxelize (2 + 8 incl. memsets) + per level rulebooks are counted in bench; here conv/BN ops
+        return self._n_launch_fwd + self._n_launch_bwd + 3

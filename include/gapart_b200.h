@@ -33,6 +33,8 @@ extern "C" {
 int gp_version(void);
 const char* gp_last_error(void);
 int gp_device_sms(void);
+/* number of CUDA kernels this library has launched (or captured into a graph) so far */
+long long gp_launch_count(void);
 int gp_fill_i32(int* p, long long n, int value, void* stream);
 int gp_memset(void* p, int byte, long long nbytes, void* stream);
 
@@ -111,20 +113,21 @@ int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, in
 /* (norm_fn gapartnet/network/model.py:86; ResBlock.forward gapartnet/network/backbone.py:40-49) */
 int gp_col_stats(const float* Y, int ldy, int C, const int* d_n, int max_n, double* stats,
                  void* stream);
+/* use_running != 0: eval mode (scale/shift from running stats, no update) */
 int gp_bn_finalize(const double* stats, int C, const int* d_n, int max_n, const float* gamma,
                    const float* beta, float eps, float momentum, float* running_mean,
-                   float* running_var, float* scale, float* shift, float* mean, float* invstd,
-                   void* stream);
+                   float* running_var, int use_running, float* scale, float* shift, float* mean,
+                   float* invstd, void* stream);
 /* Out = [relu](Y*scale + shift [+ residual]) */
 int gp_bn_apply(const float* Y, int ldy, int C, const int* d_n, int max_n, const float* scale,
                 const float* shift, const float* residual, int ldr, int relu, float* Out, int ldo,
                 void* stream);
 /* dz = dA * (A > 0) (A == NULL: no ReLU); dY = BN backward of dz; dRes (optional) (+)= dz;
- * dgamma/dbeta (optional) += ; sums: double[2C] scratch. */
+ * dgamma/dbeta (optional) += ; sums: double[2C] scratch (zeroed here iff zero_sums). */
 int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const float* Y, int ldy, int C,
               const int* d_n, int max_n, const float* mean, const float* invstd, const float* gamma,
               double* sums, float* dY, int lddy, float* dRes, int ldres, int res_accumulate,
-              float* dgamma, float* dbeta, void* stream);
+              float* dgamma, float* dbeta, int zero_sums, void* stream);
 
 /* ---- voxel <-> point rows (pc_feature = features[pc_voxel_id], network/model.py:153,359,394) -- */
 int gp_gather_rows(const float* F, int ldf, int C, const int* idx, int N, float* Out, int ldo,

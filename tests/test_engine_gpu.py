@@ -1,0 +1,122 @@
+"""GPU parity of the fused engine (points -> voxelize -> rulebooks -> U-Net fwd/bwd -> per-point
+features) against the oracle pipeline: apply_voxelization per scene (dataset/gapartnet.py:179-205)
+-> PointCloud.collate (structure/point_cloud.py:139-170) -> SparseUNet (backbone.py) ->
+features[pc_voxel_id] (model.py:153)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from gapartnet_b200 import synthetic
+from gapartnet_b200.engine import SparseUNetEngine
+from gapartnet_b200.network import backbone as mirror
+from oracle import spconv_cpu as osp
+from oracle import voxelize as ovox
+
+from util import collate_np, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_pipeline(scs, voxel, min_shape, o_net, dtype):
+    scenes = []
+    for sc in scs:
+        vf, vc, pcid, rng = ovox.apply_voxelization(sc.points, [voxel] * 3, min_shape=min_shape)
+        scenes.append(dict(vf=vf, vc=vc, pcid=pcid, shape=rng))
+    feats, idx, shape, pcid = collate_np(scenes)
+    x = osp.SparseConvTensor(torch.from_numpy(feats).to(dtype), torch.from_numpy(idx), shape, len(scs))
+    y = o_net(x).features
+    return y[torch.from_numpy(pcid)], idx, shape
+
+
+@pytest.mark.parametrize("chans,graph", [([16, 32, 48], False), ([16, 32, 48, 64, 80], True)])
+def test_engine_matches_oracle(cuda, chans, graph):
+    import gapartnet_b200.spconv.pytorch as sp
+
+    B, n, voxel, S = 3, 3000, 0.04, 64
+    scs = [synthetic.planes(40 + b, n) for b in range(B)]
+    torch.manual_seed(11)
+    o_net = mirror.build_sparse_unet(osp, 6, chans, 2)
+    o64 = copy.deepcopy(o_net).double()
+    g_net = mirror.build_sparse_unet(sp, 6, chans, 2).to(cuda)
+    g_net.load_state_dict(o_net.state_dict())
+
+    po, idx, shape = _oracle_pipeline(scs, voxel, S, o_net, torch.float32)
+    p64, _, _ = _oracle_pipeline(scs, voxel, S, o64, torch.float64)
+    assert shape == [S, S, S]
+
+    eng = SparseUNetEngine(g_net, batch=B, max_points=B * n, spatial_shape=(S, S, S), voxel_size=voxel,
+                           in_channels=6)
+    pts = torch.from_numpy(np.concatenate([s.points for s in scs])).to(cuda)
+    off = torch.arange(B + 1, dtype=torch.int64, device=cuda) * n
+    w = torch.randn(chans[0], 5, generator=torch.Generator().manual_seed(1))
+
+    eng.load_points(pts, off)
+    if graph:
+        # warm up on a side stream, then capture voxelize + rulebooks + forward in a CUDA graph
+        momentum = eng.momentum
+        eng.momentum = 0.0           # warm-up must not advance the running statistics
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            eng.build_levels()
+            eng.run_forward()
+            eng.run_backward()
+        torch.cuda.current_stream().wait_stream(s)
+        eng.momentum = momentum
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eng.build_levels()
+            eng.run_forward()
+        g.replay()
+        eng.zero_grad()
+    else:
+        eng.zero_grad()
+        eng.build_levels()
+        eng.run_forward()
+    pg = eng.pc_feature
+    assert eng.level_counts()[0] == idx.shape[0]
+    assert rel_err(pg, p64) < 1e-3
+
+    (po @ w).square().mean().backward()
+    (p64 @ w.double()).square().mean().backward()
+    pgl = pg.detach().clone().requires_grad_(True)
+    (pgl @ w.to(cuda)).square().mean().backward()
+    eng.d_pc_feature.copy_(pgl.grad)
+    eng.run_backward()
+    for (name, p64_), p32, pgp in zip(o64.named_parameters(), o_net.parameters(), g_net.parameters()):
+        e_gpu, e_cpu = rel_err(pgp.grad, p64_.grad), rel_err(p32.grad, p64_.grad)
+        assert e_gpu < max(5e-3, 4 * e_cpu + 1e-4), (name, e_gpu, e_cpu)
+    # BN running statistics advance exactly like torch's (momentum 0.1, unbiased variance)
+    for (name, b64), bg in zip(o64.named_buffers(), g_net.buffers()):
+        if "running" in name:
+            assert rel_err(bg, b64) < 1e-3, name
+
+
+def test_engine_eval_mode_uses_running_stats(cuda):
+    import gapartnet_b200.spconv.pytorch as sp
+
+    B, n, voxel, S = 2, 2000, 0.05, 32
+    scs = [synthetic.planes(60 + b, n) for b in range(B)]
+    torch.manual_seed(3)
+    o_net = mirror.build_sparse_unet(osp, 6, [16, 32], 1)
+    with torch.no_grad():
+        for m in o_net.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.uniform_(-0.2, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+    g_net = mirror.build_sparse_unet(sp, 6, [16, 32], 1).to(cuda)
+    g_net.load_state_dict(o_net.state_dict())
+    o_net.eval()
+    with torch.no_grad():
+        po, idx, shape = _oracle_pipeline(scs, voxel, S, o_net, torch.float32)
+    eng = SparseUNetEngine(g_net, batch=B, max_points=B * n, spatial_shape=(S, S, S), voxel_size=voxel, in_channels=6)
+    eng.training = False
+    pts = torch.from_numpy(np.concatenate([s.points for s in scs])).to(cuda)
+    off = torch.arange(B + 1, dtype=torch.int64, device=cuda) * n
+    pg = eng.forward_points(pts, off)
+    assert rel_err(pg, po) < 1e-4
+    for (name, bo), bg in zip(o_net.named_buffers(), g_net.buffers()):
+        if "running" in name:
+            assert torch.equal(bg.cpu(), bo), name
