@@ -211,6 +211,15 @@ def run_ours(args):
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     counts = eng.level_counts()
+    if args.ncu_step:
+        # exactly one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_body()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"ncu_step": True, "level_rows": counts}))
+        return
     use_graph = not args.no_graph
     graph = None
     l0 = C.gp_launch_count()
@@ -418,6 +427,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

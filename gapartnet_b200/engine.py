@@ -53,7 +53,8 @@ class SparseUNetEngine:
 
     def __init__(self, net: nn.Module, batch: int, max_points: int, spatial_shape: Sequence[int],
                  voxel_size: float, in_channels: int, max_rows: Optional[Sequence[int]] = None,
-                 input_needs_grad: bool = False, bn_eps: float = 1e-4, bn_momentum: float = 0.1):
+                 input_needs_grad: bool = False, bn_eps: float = 1e-4, bn_momentum: float = 0.1,
+                 use_tc: Optional[bool] = None):
         p0 = next(net.parameters())
         if not p0.is_cuda:
             raise GapartError("SparseUNetEngine needs the module on a CUDA device")
@@ -125,6 +126,9 @@ class SparseUNetEngine:
         self._stat_arena = None
         self._stat_used = 0
         self._keep: List[torch.Tensor] = []
+        self.use_tc = ops.USE_TC if use_tc is None else bool(use_tc)
+        self._ws_floats = 0
+        self._ws = None
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -200,10 +204,21 @@ class SparseUNetEngine:
         res_ptr, res_ld = (residual.ptr, residual.ld) if residual is not None else (None, 0)
         eng = self
 
+        tc_f = eng.use_tc and bool(C.gp_conv_tc_supported(Cin, Cout, K, x.ld, y.ld))
+        tc_b = eng.use_tc and bool(C.gp_conv_tc_supported(Cout, Cin, K, y.ld, x.ld))
+        if tc_f or tc_b:
+            eng._ws_floats = max(eng._ws_floats, int(C.gp_conv_tc_workspace_floats(K, Cin, Cout)),
+                                 int(C.gp_conv_tc_workspace_floats(K, Cout, Cin)))
+
         def fwd():
             s = eng._s()
-            C.gp_conv_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                          y.ptr, y.ld, Cout, 0, _p(stats) if eng.training else None, s)
+            st = _p(stats) if eng.training else None
+            if tc_f:
+                C.gp_conv_tc_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
+                                 y.ptr, y.ld, Cout, 0, st, _p(eng._ws), s)
+            else:
+                C.gp_conv_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
+                              y.ptr, y.ld, Cout, 0, st, s)
             C.gp_bn_finalize(_p(stats), Cout, _p(d_n_out), n_out, g_ptr, b_ptr, eng.eps, eng.momentum,
                              rm_ptr, rv_ptr, 0 if eng.training else 1, sc, sh, mu, istd, s)
             C.gp_bn_apply(y.ptr, y.ld, Cout, _p(d_n_out), n_out, sc, sh, res_ptr, res_ld, int(relu),
@@ -240,8 +255,12 @@ class SparseUNetEngine:
                             mu, istd, g_ptr, _p(sums), dy.ptr, dy.ld, dres_ptr, dres_ld, dres_acc,
                             gg_ptr, bg_ptr, 0, s)
                 if dx_ptr is not None:
-                    C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
-                                  _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
+                    if tc_b and dx_ld % 4 == 0:
+                        C.gp_conv_tc_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
+                                         _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, _p(eng._ws), s)
+                    else:
+                        C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
+                                      _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
                 C.gp_conv_wgrad(x.ptr, x.ld, Cin, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
                                 wg_ptr, Cin, 1, K * Cin, 0, s)
 
@@ -359,6 +378,7 @@ class SparseUNetEngine:
         out.grad_ready = True
         self.pc_feature = torch.empty(self.N, out.C, dtype=torch.float32, device=self.dev)
         self.d_pc_feature = torch.zeros(self.N, out.C, dtype=torch.float32, device=self.dev)
+        self._ws = torch.empty(max(self._ws_floats, 4), dtype=torch.float32, device=self.dev)
         # reverse pass: instantiate backward closures in execution order
         self._bwd = []
         for mk in reversed(self._bwd_units):

@@ -5,6 +5,7 @@ There is deliberately no CPU implementation here: a non-CUDA tensor raises.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -182,11 +183,25 @@ def rulebook_down2(coords4: torch.Tensor, n_in: int, batch: int, shape: Sequence
 # ---------------------------------------------------------------------------------------------
 # convolution primitives (weights in spconv's KRSC layout [Cout, K, Cin])
 # ---------------------------------------------------------------------------------------------
+_TC_WS = {}
+USE_TC = os.environ.get("GAPART_TC", "1") != "0"
+
+
+def tc_workspace(device, floats: int) -> torch.Tensor:
+    """scratch for the pre-swizzled weight images of the tensor-core conv (reused stream-ordered)"""
+    ws = _TC_WS.get(device)
+    if ws is None or ws.numel() < floats:
+        ws = torch.empty(max(floats, 1 << 20), dtype=torch.float32, device=device)
+        _TC_WS[device] = ws
+    return ws
+
+
 def conv_fwd(x: torch.Tensor, w_krsc: torch.Tensor, table: Optional[torch.Tensor], K: int, n_out: int,
              d_n_out: Optional[torch.Tensor] = None, *, transpose: bool = False, flip: bool = False,
              out: Optional[torch.Tensor] = None, accumulate: bool = False,
-             stats: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = conv(x). transpose=True computes the input gradient operator (W^T)."""
+             stats: Optional[torch.Tensor] = None, use_tc: Optional[bool] = None) -> torch.Tensor:
+    """y = conv(x). transpose=True computes the input gradient operator (W^T).
+    use_tc: None = tcgen05 path when the shape qualifies (GAPART_TC=0 forces the SIMT path)."""
     _need_cuda(x, w_krsc)
     assert x.dtype == torch.float32 and x.stride(1) == 1 and w_krsc.is_contiguous()
     Cout_w, Cin_w = w_krsc.shape[0], w_krsc.shape[-1]
@@ -202,9 +217,18 @@ def conv_fwd(x: torch.Tensor, w_krsc: torch.Tensor, table: Optional[torch.Tensor
         out = torch.empty(max(n_out, 0), cout, dtype=torch.float32, device=x.device)
     tstride = table.shape[1] if table is not None else 0
     if n_out > 0:
-        C.gp_conv_fwd(_p(x), x.stride(0), cin, _p(w_krsc), w_sk, w_sci, w_sco, int(flip), _p(table),
-                      tstride, K, _p(d_n_out), n_out, _p(out), out.stride(0), cout, int(accumulate),
-                      _p(stats), _stream())
+        tc = USE_TC if use_tc is None else use_tc
+        tc = tc and bool(C.gp_conv_tc_supported(cin, cout, K, x.stride(0), out.stride(0))) \
+            and x.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0
+        if tc:
+            ws = tc_workspace(x.device, int(C.gp_conv_tc_workspace_floats(K, cin, cout)))
+            C.gp_conv_tc_fwd(_p(x), x.stride(0), cin, _p(w_krsc), w_sk, w_sci, w_sco, int(flip), _p(table),
+                             tstride, K, _p(d_n_out), n_out, _p(out), out.stride(0), cout, int(accumulate),
+                             _p(stats), _p(ws), _stream())
+        else:
+            C.gp_conv_fwd(_p(x), x.stride(0), cin, _p(w_krsc), w_sk, w_sci, w_sco, int(flip), _p(table),
+                          tstride, K, _p(d_n_out), n_out, _p(out), out.stride(0), cout, int(accumulate),
+                          _p(stats), _stream())
     return out
 
 

@@ -1,0 +1,121 @@
+"""GPU: the tcgen05 (3xTF32) implicit-GEMM conv against the exact-fp32 SIMT path and an fp64 torch
+reference, over the channel/tap shapes of the GAPartNet U-Net, strided concat buffers, device-side
+row counts, accumulate and the fused BatchNorm statistics."""
+import numpy as np
+import pytest
+import torch
+
+from gapartnet_b200 import ops
+from oracle import rulebook as rb
+
+from util import collate_np, rel_err, small_scene_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(cuda, n=6000, voxel=0.03, batch=2, seed=5):
+    scenes = small_scene_batch(batch, n, voxel, seed0=seed, min_shape=64)
+    feats, idx, shape, _ = collate_np(scenes)
+    nbr = rb.subm3_table(idx, shape)
+    out, so, child, parent8 = rb.down2_tables(idx, shape)
+    return dict(M=idx.shape[0], nbr=torch.from_numpy(nbr).to(cuda), child=torch.from_numpy(child).to(cuda),
+                parent8=torch.from_numpy(parent8).to(cuda), Mo=out.shape[0])
+
+
+def _ref(x, w, table, K, n_out, transpose=False, flip=False):
+    """fp64 reference on the GPU with torch ops"""
+    x = x.double()
+    w = w.double()  # [Cout, K, Cin]
+    cout = w.shape[2] if transpose else w.shape[0]
+    y = torch.zeros(n_out, cout, dtype=torch.float64, device=x.device)
+    for k in range(K):
+        t = table[k, :n_out].long() if table is not None else torch.arange(n_out, device=x.device)
+        ok = t >= 0
+        kw = K - 1 - k if flip else k
+        wk = w[:, kw, :] if transpose else w[:, kw, :].t()  # [in, out]
+        y[ok] += x[t[ok]] @ wk
+    return y
+
+
+SHAPES = [(16, 16), (32, 16), (16, 32), (32, 32), (48, 48), (64, 64), (80, 80), (96, 112), (112, 112), (224, 112),
+          (112, 224), (192, 96)]
+
+
+@pytest.mark.parametrize("cin,cout", SHAPES)
+def test_tc_subm3_matches_fp64(cuda, cin, cout):
+    t = _table(cuda)
+    M = t["M"]
+    g = torch.Generator(device="cpu").manual_seed(cin * 1000 + cout)
+    x = torch.randn(M, cin, generator=g).to(cuda)
+    w = (torch.randn(cout, 27, cin, generator=g) * 0.1).to(cuda)
+    y_tc = ops.conv_fwd(x, w, t["nbr"], 27, M, use_tc=True)
+    y_si = ops.conv_fwd(x, w, t["nbr"], 27, M, use_tc=False)
+    ref = _ref(x, w, t["nbr"], 27, M)
+    assert rel_err(y_si, ref) < 2e-6
+    assert rel_err(y_tc, ref) < 2e-5, "3xTF32 should be fp32-accurate"
+    # dgrad operator: transposed weights + flipped taps
+    dy = torch.randn(M, cout, generator=g).to(cuda)
+    dx_tc = ops.conv_fwd(dy, w, t["nbr"], 27, M, transpose=True, flip=True, use_tc=True)
+    assert rel_err(dx_tc, _ref(dy, w, t["nbr"], 27, M, transpose=True, flip=True)) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["k1", "down", "up"])
+def test_tc_other_tables(cuda, kind):
+    t = _table(cuda)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    if kind == "k1":
+        x = torch.randn(t["M"], 64, generator=g).to(cuda)
+        w = (torch.randn(32, 1, 64, generator=g) * 0.1).to(cuda)
+        y = ops.conv_fwd(x, w, None, 1, t["M"], use_tc=True)
+        assert rel_err(y, _ref(x, w, None, 1, t["M"])) < 2e-5
+    elif kind == "down":
+        x = torch.randn(t["M"], 32, generator=g).to(cuda)
+        w = (torch.randn(48, 8, 32, generator=g) * 0.1).to(cuda)
+        y = ops.conv_fwd(x, w, t["child"], 8, t["Mo"], use_tc=True)
+        assert rel_err(y, _ref(x, w, t["child"], 8, t["Mo"])) < 2e-5
+    else:
+        x = torch.randn(t["Mo"], 48, generator=g).to(cuda)
+        w = (torch.randn(32, 8, 48, generator=g) * 0.1).to(cuda)
+        y = ops.conv_fwd(x, w, t["parent8"], 8, t["M"], use_tc=True)
+        assert rel_err(y, _ref(x, w, t["parent8"], 8, t["M"])) < 2e-5
+
+
+@pytest.mark.parametrize("n_rows", [1, 127, 128, 129, 1000])
+def test_tc_ragged_rows_device_count_stats_accumulate(cuda, n_rows):
+    """rows not a multiple of 128, row count read from the device, strided (concat) buffers,
+    accumulate into an existing output and the BN sum / sum-of-squares epilogue."""
+    t = _table(cuda, n=3000)
+    M = t["M"]
+    assert n_rows <= M
+    g = torch.Generator(device="cpu").manual_seed(n_rows)
+    xcat = torch.randn(M, 64, generator=g).to(cuda)
+    x = xcat[:, 32:]                       # strided view: ld = 64, C = 32
+    w = (torch.randn(16, 27, 32, generator=g) * 0.1).to(cuda)
+    ycat = torch.randn(M, 48, generator=g).to(cuda)
+    y0 = ycat.clone()
+    out = ycat[:, 16:32]                   # ld = 48
+    d_n = torch.tensor([n_rows], dtype=torch.int32, device=cuda)
+    stats = torch.zeros(32, dtype=torch.float64, device=cuda)
+    ops.conv_fwd(x, w, t["nbr"], 27, M, d_n_out=d_n, out=out, accumulate=True, stats=stats, use_tc=True)
+    ref = _ref(x, w, t["nbr"][:, :], 27, M)[:n_rows] + y0[:n_rows, 16:32].double()
+    assert rel_err(out[:n_rows], ref) < 2e-5
+    # rows beyond the device count and the neighbouring columns are untouched
+    assert torch.equal(ycat[n_rows:], y0[n_rows:])
+    assert torch.equal(ycat[:, :16], y0[:, :16]) and torch.equal(ycat[:, 32:], y0[:, 32:])
+    assert rel_err(stats[:16], ref.sum(0)) < 1e-5
+    assert rel_err(stats[16:], (ref * ref).sum(0)) < 1e-5
+
+
+def test_tc_many_tiles_persistent(cuda):
+    """more row tiles than SMs: exercises the persistent loop, stage ring wrap-around and both
+    TMEM accumulator buffers"""
+    scenes = small_scene_batch(4, 20000, 0.02, seed0=77, min_shape=128)
+    feats, idx, shape, _ = collate_np(scenes)
+    M = idx.shape[0]
+    assert M > 128 * 200
+    nbr = torch.from_numpy(rb.subm3_table(idx, shape)).to(cuda)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn(M, 16, generator=g).to(cuda)
+    w = (torch.randn(16, 27, 16, generator=g) * 0.1).to(cuda)
+    y = ops.conv_fwd(x, w, nbr, 27, M, use_tc=True)
+    assert rel_err(y, _ref(x, w, nbr, 27, M)) < 2e-5
