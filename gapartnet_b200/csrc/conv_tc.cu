@@ -13,14 +13,17 @@
 // (10-bit mantissa).  We use the 3xTF32 split: a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits),
 //   D += a_hi*b_hi + a_lo*b_hi + a_hi*b_lo          (error ~2^-21, fp32 accumulate in TMEM)
 //
-// Warp roles (416 threads, 1 CTA/SM, persistent over row tiles):
-//   warps 0-3   epilogue: tcgen05.ld accumulator -> (+= old) -> global rows, BN sum/sumsq
-//   warps 4-11  producers: cp.async gather of raw fp32 rows straight into the 128B-swizzled UMMA
-//               tile, then in-place hi/lo split (the thread that copied a 16-byte piece converts it)
-//   warp  12    one elected thread issues tcgen05.mma.kind::tf32 (12 per chunk) and the commits
-// Weights are pre-split and pre-swizzled into per-chunk smem images by k_pack_weights and fetched
-// with one cp.async.bulk (TMA 1-D) per chunk.  Pipelines: smem full/empty mbarriers per stage,
-// TMEM full/empty per accumulator buffer (double buffered, epilogue overlaps the next tile).
+// Warp roles (448 threads, 1 CTA/SM, persistent over 128-row tiles), see k_conv_tc:
+//   epilogue x4 | gather x4 (cp.async, zero-fill) | convert x4 (hi/lo split -> TMEM A operand) |
+//   MMA issuer x1 (tcgen05.mma kind::tf32, A from TMEM, B from smem) | weight loader x1 (TMA bulk)
+// Weights are pre-split and pre-swizzled into per-chunk smem images by k_pack_weights.
+// Pipelines: per-stage mbarriers empty -> raw_full/b_full -> a_full -> (commit) empty, and
+// full/empty per TMEM accumulator buffer (double buffered: the epilogue overlaps the next tile).
+// Measured lessons kept in the code: mbarrier hops cost ~400 cycles, so every role runs ahead on
+// its own (stage, phase) counters; integer division and lane-divergent MMA issue (R2UR waterfall)
+// each cost >1k cycles per chunk and are gone; GAPART_TC_TS=<device ptr> records a clock64 trace.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/gapart_b200.h"
 
@@ -28,7 +31,7 @@
 #define TC_KCHUNK 32                      // floats per chunk = 128 bytes
 #define TC_A_TILE (TC_ROWS * 128)         // bytes of one A tile (hi or lo)
 #define TC_PRODUCERS 256
-#define TC_THREADS 416
+#define TC_THREADS 448
 #define TC_MAX_TAPS 27
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -61,6 +64,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// mbarrier operations are per-thread shared-memory transactions: 128 threads polling one barrier
+// cost ~1.4k cycles per chunk (measured).  Waits are therefore warp-uniform: lane 0 polls, the
+// warp re-converges on __syncwarp (which also orders the other lanes' later accesses).
+#define TC_TS(ev, g) do { if (p.ts && blockIdx.x == 0 && lane == 0 && (tid == 160 || tid == 256 || tid == 384) && (g) < 256) p.ts[(ev) * 256 + (g)] = clock64(); } while (0)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+// one elected lane of a converged warp (elect.sync): unlike `lane == 0` the compiler keeps the
+// operands of the guarded tcgen05 instructions in uniform registers (no R2UR waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -134,192 +155,291 @@ struct TcParams {
     const int* d_n_out; int max_out;
     float* Y; int ldy; int Cout; int accumulate;
     double* stats;
-    int n_chunks; int stages; int tmem_cols;
+    int n_chunks; int stages; int nbuf; int accw;
+    long long* ts;   // optional timestamp trace [6][256] of CTA 0 (perf experiments)
 };
 
+#define TC_TMEM_COLS 512
+#define TC_GATHERERS 128
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]),
+        "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]),
+        "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        : "memory");
+}
+
+// Warp roles (416 threads, 1 CTA/SM, persistent over 128-row tiles):
+//   warps 0-3   epilogue : tcgen05.ld accumulator -> (+= old) -> global rows, BN sum/sumsq
+//   warps 4-7   gather   : cp.async (16 B, zero-fill for absent neighbours) of raw fp32 rows into a
+//                          128B-swizzled smem tile; completion is signalled by the copies themselves
+//                          (cp.async.mbarrier.arrive.noinc) so these threads never wait on data
+//   warps 8-11  convert  : thread = row = TMEM lane: 8 conflict-free LDS.128 of its row, hi/lo split,
+//                          two tcgen05.st into the A operand region of tensor memory
+//   warp  12    MMA      : one thread issues tcgen05.mma.kind::tf32 with A from TMEM, B (weights)
+//                          from smem; 12 MMAs per 32-wide K chunk (3xTF32)
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stage tiles][idx double buffer][stats][barriers]
     const int Cout = p.Cout;
-    const uint32_t b_bytes = (uint32_t)Cout * 256;            // hi + lo image of one chunk
-    const uint32_t stage_bytes = 2 * TC_A_TILE + b_bytes;
+    const uint32_t b_bytes = (uint32_t)Cout * 256;            // hi + lo weight image of one chunk
+    const uint32_t stage_bytes = TC_A_TILE + b_bytes;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
     int* s_idx = reinterpret_cast<int*>(tiles + (size_t)p.stages * stage_bytes);          // [2][Ktaps][128]
     double* s_stats = reinterpret_cast<double*>(s_idx + 2 * p.Ktaps * TC_ROWS);           // [2][Cout]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + 2 * Cout);
-    uint64_t* full = bars;                      // [stages]
-    uint64_t* empty = bars + p.stages;          // [stages]
-    uint64_t* acc_full = empty + p.stages;      // [2]
-    uint64_t* acc_empty = acc_full + 2;         // [2]
+    const int S = p.stages;
+    uint64_t* empty = bars;                 // [S]  MMA done with smem stage + TMEM A stage
+    uint64_t* raw_full = bars + S;          // [S]  gathered rows landed in smem
+    uint64_t* b_full = bars + 2 * S;        // [S]  weight image landed in smem
+    uint64_t* a_full = bars + 3 * S;        // [S]  hi/lo operand written to TMEM
+    uint64_t* acc_full = bars + 4 * S;      // [2]
+    uint64_t* acc_empty = acc_full + 2;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_out = gp_rows(p.d_n_out, p.max_out);
     const int n_tiles = (n_out + TC_ROWS - 1) / TC_ROWS;
-    const int S = p.stages;
+    const int nbuf = p.nbuf;
+    const uint32_t accw = (uint32_t)p.accw;
+    const uint32_t a_base = (uint32_t)nbuf * accw;            // first TMEM column of the A stages
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], 8 + 1);   // 8 producer warps + the expect_tx arrive of the weight copy
-            mbar_init(&empty[s], 1);      // tcgen05.commit
+            mbar_init(&empty[s], 1);
+            mbar_init(&raw_full[s], TC_GATHERERS);   // noinc arrive of every gather thread
+            mbar_init(&b_full[s], 1);
+            mbar_init(&a_full[s], 4);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4);  // one arrive per epilogue warp
+            mbar_init(&acc_empty[b], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 2 * Cout; i += TC_THREADS) s_stats[i] = 0.0;
     if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)p.tmem_cols));
+                     "r"((uint32_t)TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t acc_cols = (uint32_t)p.tmem_cols >> 1;  // columns per accumulator buffer
 
-    if (warp >= 4 && warp < 12) {
-        // ===================== producers: gather + hi/lo split =====================
-        const int ptid = tid - 128;
-        const int j = ptid & 7;          // 16-byte piece within the 128-byte chunk row
-        const int r0 = ptid >> 3;        // rows r0, r0+32, r0+64, r0+96
-        const int D = S - 1;             // cp.async groups in flight
-        const int kk0 = j * 4;           // GEMM-K offset of this piece inside a chunk
-        long long g = 0;                 // running chunk counter (stage / phase bookkeeping)
-        const long long my_tiles = (n_tiles > (int)blockIdx.x) ? ((n_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
-        const long long total = my_tiles * p.n_chunks;
-        int tile = blockIdx.x;
-        int c = 0;  // chunk within tile
-        for (long long it = 0; it < total + D; ++it) {
-            if (it < total) {
-                if (c == 0) {
-                    // index tile of this row tile -> smem (double buffered by tile parity)
-                    int* idx_t = s_idx + ((it / p.n_chunks) & 1) * p.Ktaps * TC_ROWS;
-                    for (int e = ptid; e < p.Ktaps * TC_ROWS; e += TC_PRODUCERS) {
-                        int k = e >> 7, r = e & 127;
-                        int row = tile * TC_ROWS + r;
-                        int v = -1;
-                        if (row < n_out) v = p.nbr ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row) : row;
-                        idx_t[e] = v;
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"r"(TC_PRODUCERS) : "memory");
-                }
-                const int* idx_t = s_idx + ((it / p.n_chunks) & 1) * p.Ktaps * TC_ROWS;
-                const int stage = (int)(g % S);
-                const uint32_t ph = (uint32_t)((g / S) & 1);
-                mbar_wait(&empty[stage], ph ^ 1);
+    if (warp >= 4 && warp < 8) {
+        // ===================== gather: global -> smem (raw fp32, swizzled) =====================
+        // Fully decoupled from consumption: the copies themselves arm raw_full (noinc arrive), so
+        // these warps run up to S chunks ahead and never wait on data.  No integer division in the
+        // loop: (stage, phase) and (tap, ci) advance incrementally.
+        const int gt = tid - 128;
+        const int j = gt & 7;            // 16-byte piece within the 128-byte chunk row
+        const int r0 = gt >> 3;          // rows r0 + 16*i
+        int stage = 0;
+        uint32_t ph = 0;
+        int titer = 0;
+        const int n_idx = p.Ktaps * TC_ROWS;
+        const int Q = (p.Ktaps + p.n_chunks - 1) / p.n_chunks;   // index prefetches per thread per chunk
+        auto load_idx = [&](int* dst, int t, int e) {
+            int k = e >> 7, r = e & 127;
+            int row = t * TC_ROWS + r;
+            int v = -1;
+            if (row < n_out) v = p.nbr ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row) : row;
+            dst[e] = v;
+        };
+        if ((int)blockIdx.x < n_tiles) {
+            for (int e = gt; e < n_idx; e += TC_GATHERERS) load_idx(s_idx, blockIdx.x, e);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(TC_GATHERERS) : "memory");
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+            int* idx_t = s_idx + (titer & 1) * n_idx;
+            int* idx_next = s_idx + ((titer + 1) & 1) * n_idx;
+            const int next_tile = tile + gridDim.x;
+            // position of this thread's piece on the GEMM-K axis: kk = c*32 + 4j = tap*Cin + ci
+            int tap = (4 * j) / p.Cin, ci = 4 * j - tap * p.Cin;
+            for (int c = 0; c < p.n_chunks; ++c) {
+                mbar_wait_warp(&empty[stage], ph ^ 1, lane);
+                TC_TS(0, c);
                 uint8_t* st = tiles + (size_t)stage * stage_bytes;
-                if (ptid == 0) {
-                    // weights of this chunk: one TMA bulk copy, completes on the stage's full barrier
-                    mbar_arrive_expect_tx(&full[stage], b_bytes);
+                const bool tap_ok = tap < p.Ktaps;
+                int idx[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) idx[i] = tap_ok ? idx_t[tap * TC_ROWS + r0 + 16 * i] : -1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float* src = p.X + (idx[i] >= 0 ? ((size_t)idx[i] * p.ldx + ci) : 0);
+                    uint32_t nbytes = idx[i] >= 0 ? 16u : 0u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                                     smem_u32(st + swz128(r0 + 16 * i, j))),
+                                 "l"(src), "r"(nbytes));
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[stage]))
+                             : "memory");
+                TC_TS(1, c);
+                if (next_tile < n_tiles) {
+                    // spread the next tile's neighbour-index loads over this tile's chunks
+                    for (int q = 0; q < Q; ++q) {
+                        int e = (c * Q + q) * TC_GATHERERS + gt;
+                        if (e < n_idx) load_idx(idx_next, next_tile, e);
+                    }
+                }
+                ci += TC_KCHUNK;
+                while (ci >= p.Cin) {
+                    ci -= p.Cin;
+                    ++tap;
+                }
+                if (++stage == S) {
+                    stage = 0;
+                    ph ^= 1;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(TC_GATHERERS) : "memory");   // next index tile complete
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp == 13) {
+        // ===================== weight loader: one TMA bulk copy per chunk =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    mbar_wait(&empty[stage], ph ^ 1);
+                    mbar_arrive_expect_tx(&b_full[stage], b_bytes);
                     const float* src = p.Wpack + (size_t)c * Cout * 64;
                     asm volatile(
                         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                            smem_u32(st + 2 * TC_A_TILE)),
-                        "l"(src), "r"(b_bytes), "r"(smem_u32(&full[stage]))
+                            smem_u32(tiles + (size_t)stage * stage_bytes + TC_A_TILE)),
+                        "l"(src), "r"(b_bytes), "r"(smem_u32(&b_full[stage]))
                         : "memory");
-                }
-                const int kk = c * TC_KCHUNK + kk0;
-                const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
-                const bool tap_ok = tap < p.Ktaps;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = r0 + 32 * i;
-                    int idx = tap_ok ? idx_t[tap * TC_ROWS + r] : -1;
-                    const float* src = p.X + (idx >= 0 ? ((size_t)idx * p.ldx + ci) : 0);
-                    uint32_t nbytes = idx >= 0 ? 16u : 0u;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(st + swz128(r, j))),
-                                 "l"(src), "r"(nbytes)
-                                 : "memory");
-                }
-                ++g;
-                if (++c == p.n_chunks) {
-                    c = 0;
-                    tile += gridDim.x;
+                    if (++stage == S) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (it >= D) {
-                // the group issued D iterations ago has landed: split it in place
-                switch (D) {
-                    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-                    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-                    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-                    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-                    default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-                }
-                const long long h = it - D;
-                const int stage = (int)(h % S);
-                uint8_t* st = tiles + (size_t)stage * stage_bytes;
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ===================== convert: smem -> registers -> hi/lo -> TMEM =====================
+        const int row = tid - 256;       // 0..127 = TMEM lane
+        const uint32_t lane_base = (uint32_t)((warp - 8) * 32) << 16;
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int c = 0; c < p.n_chunks; ++c) {
+                mbar_wait_warp(&raw_full[stage], ph, lane);
+                TC_TS(2, c);
+                const uint8_t* st = tiles + (size_t)stage * stage_bytes;
+                float v[32], h[32];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t off = swz128(r0 + 32 * i, j);
-                    float4 v = *reinterpret_cast<float4*>(st + off);
-                    float4 hi, lo;
-                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-                    *reinterpret_cast<float4*>(st + off) = hi;
-                    *reinterpret_cast<float4*>(st + TC_A_TILE + off) = lo;
+                for (int q = 0; q < 8; ++q) {
+                    float4 t = *reinterpret_cast<const float4*>(st + swz128(row, q));
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic -> async proxy
+#pragma unroll
+                for (int e = 0; e < 32; ++e) h[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+                const uint32_t taddr = tmem_base + lane_base + a_base + (uint32_t)stage * 64;
+                tmem_st32(taddr, h);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] -= h[e];
+                tmem_st32(taddr + 32, v);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);
+                if (lane == 0) mbar_arrive(&a_full[stage]);
+                TC_TS(3, c);
+                if (++stage == S) {
+                    stage = 0;
+                    ph ^= 1;
+                }
             }
         }
     } else if (warp == 12) {
         // ===================== MMA issuer =====================
+        // every operand below is warp-uniform (made explicit with shfl) so the elected lane issues
+        // UTCHMMA straight from uniform registers
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Cout >> 3) << 17) |
                                ((uint32_t)(TC_ROWS >> 4) << 24);
-        long long g = 0;
-        int titer = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
-            const int buf = titer & 1;
-            mbar_wait(&acc_empty[buf], (uint32_t)(((titer >> 1) & 1) ^ 1));
+        const uint32_t tbase = uniform(tmem_base);
+        const uint32_t tiles_u32 = uniform(smem_u32(tiles));
+        const uint32_t bars_u32 = uniform(smem_u32(bars));
+        // descriptor high word is constant: SBO = 1024 B, version 1, SWIZZLE_128B
+        const uint32_t desc_hi = (uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+        int stage = 0;
+        uint32_t ph = 0;
+        int buf = 0;
+        uint32_t acc_ph = 0;             // parity of the current use of accumulator buffer `buf`
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait_warp(&acc_empty[buf], acc_ph ^ 1, lane);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)buf * acc_cols;
-            for (int c = 0; c < p.n_chunks; ++c, ++g) {
-                const int stage = (int)(g % S);
-                mbar_wait(&full[stage], (uint32_t)((g / S) & 1));
-                tc_fence_after();
+            const uint32_t d_tmem = tbase + (uint32_t)buf * accw;
+            for (int c = 0; c < p.n_chunks; ++c) {
                 if (lane == 0) {
-                    const uint32_t a_hi = smem_u32(tiles + (size_t)stage * stage_bytes);
-                    const uint32_t a_lo = a_hi + TC_A_TILE;
-                    const uint32_t b_hi = a_hi + 2 * TC_A_TILE;
-                    const uint32_t b_lo = b_hi + (uint32_t)Cout * 128;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t da_hi = umma_desc_sw128(a_hi + ks * 32);
-                        const uint64_t da_lo = umma_desc_sw128(a_lo + ks * 32);
-                        const uint64_t db_hi = umma_desc_sw128(b_hi + ks * 32);
-                        const uint64_t db_lo = umma_desc_sw128(b_lo + ks * 32);
-                        tc_mma_tf32(d_tmem, da_hi, db_hi, idesc, (c | ks) ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
-                        tc_mma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-                    }
+                    mbar_wait(&b_full[stage], ph);
+                    mbar_wait(&a_full[stage], ph);
                 }
                 __syncwarp();
-                if (lane == 0) tc_commit(&empty[stage]);   // stage reusable once these MMAs retire
+                TC_TS(4, c);
+                tc_fence_after();
+                const uint32_t b_hi = tiles_u32 + (uint32_t)stage * stage_bytes + TC_A_TILE;
+                const uint32_t b_lo = b_hi + (uint32_t)Cout * 128;
+                const uint32_t a_hi = tbase + a_base + (uint32_t)stage * 64;
+                const uint32_t empty_bar = bars_u32 + (uint32_t)stage * 8;   // empty[] is the first array
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_hi + ks * 32) >> 4) & 0x3FFF);
+                        const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_lo + ks * 32) >> 4) & 0x3FFF);
+                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, (c | ks) ? 1u : 0u);
+                        tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
+                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_lo, idesc, 1u);
+                    }
+                    // smem + TMEM stage reusable once these retire
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     empty_bar)
+                                 : "memory");
+                }
+                __syncwarp();
+                TC_TS(5, c);
+                if (++stage == S) {
+                    stage = 0;
+                    ph ^= 1;
+                }
             }
-            if (lane == 0) tc_commit(&acc_full[buf]);
+            if (elect_one()) tc_commit(&acc_full[buf]);
             __syncwarp();
+            if (++buf == nbuf) {
+                buf = 0;
+                acc_ph ^= 1;
+            }
         }
     } else {
         // ===================== epilogue (warps 0-3) =====================
-        int titer = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
-            const int buf = titer & 1;
-            mbar_wait(&acc_full[buf], (uint32_t)((titer >> 1) & 1));
+        int buf = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait_warp(&acc_full[buf], acc_ph, lane);
             tc_fence_after();
             const int row = tile * TC_ROWS + warp * 32 + lane;
             const bool active = row < n_out;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * acc_cols;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * accw;
             float* yr = p.Y + (size_t)row * p.ldy;
             for (int c0 = 0; c0 < Cout; c0 += 16) {
                 uint32_t v[16];
@@ -402,6 +522,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (++buf == nbuf) {
+                buf = 0;
+                acc_ph ^= 1;
+            }
         }
     }
     tc_fence_before();
@@ -415,7 +539,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     }
     if (warp == 12) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)p.tmem_cols));
+                     "r"((uint32_t)TC_TMEM_COLS));
     }
 }
 
@@ -453,21 +577,27 @@ extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, 
     p.X = X; p.ldx = ldx; p.Cin = Cin; p.Wpack = wpack; p.nbr = nbr; p.tbl_stride = tbl_stride; p.Ktaps = K;
     p.d_n_out = d_n_out; p.max_out = max_out; p.Y = Y; p.ldy = ldy; p.Cout = Cout; p.accumulate = accumulate;
     p.stats = stats; p.n_chunks = n_chunks;
-    const size_t stage_bytes = 2 * TC_A_TILE + (size_t)Cout * 256;
-    const size_t fixed = 1024 /*align*/ + (size_t)2 * K * TC_ROWS * 4 + (size_t)2 * Cout * 8 + 256;
+    {
+        const char* tsp = getenv("GAPART_TC_TS");   // device pointer (decimal) of a [6*256] int64 trace buffer
+        p.ts = tsp ? (long long*)strtoull(tsp, nullptr, 10) : nullptr;
+    }
+    // tensor memory: [accumulator buffers | A operand stages of 64 columns (hi 32 + lo 32)]
+    p.accw = (Cout + 31) & ~31;
+    p.nbuf = (2 * p.accw + 2 * 64 <= TC_TMEM_COLS) ? 2 : 1;
+    const int s_tmem = (TC_TMEM_COLS - p.nbuf * p.accw) / 64;
+    const size_t stage_bytes = TC_A_TILE + (size_t)Cout * 256;
+    const size_t fixed = 1024 /*align*/ + (size_t)2 * K * TC_ROWS * 4 + (size_t)2 * Cout * 8 + 512;
     const size_t budget = 227 * 1024;
     int S = (int)((budget - fixed) / stage_bytes);
-    if (S > 6) S = 6;
-    GP_CHECK_ARG(S >= 2, "gp_conv_tc_fwd: not enough shared memory for Cout=%d", Cout);
+    if (S > s_tmem) S = s_tmem;
+    if (S > 8) S = 8;
+    GP_CHECK_ARG(S >= 2, "gp_conv_tc_fwd: not enough shared/tensor memory for Cout=%d", Cout);
     p.stages = S;
-    int cols = 32;
-    while (cols < 2 * Cout) cols <<= 1;
-    p.tmem_cols = cols;
     size_t smem = fixed + (size_t)S * stage_bytes;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    static thread_local bool configured = false;
+    if (!configured) {
         GP_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        configured = budget;
+        configured = true;
     }
     int tiles = gp_cdiv(max_out, TC_ROWS);
     int grid = tiles < gp_num_sms() ? tiles : gp_num_sms();

