@@ -192,30 +192,47 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     const bool xvec = ((ldx & 3) == 0) && (ci0 + 4 <= Cin) && ((reinterpret_cast<size_t>(X) & 15) == 0);
     const bool yvec = ((ldy & 3) == 0) && (co0 + 4 <= Cout) && ((reinterpret_cast<size_t>(dY) & 15) == 0);
-    for (int r = r0 + rg; r < r1; r += 16) {
-        int idx = nbr ? __ldg(nbr + (size_t)k * tbl_stride + r) : r;
-        if (idx < 0) continue;
-        float xv[4], yv[4];
-        const float* xr = X + (size_t)idx * ldx + ci0;
-        const float* yr = dY + (size_t)r * ldy + co0;
-        if (xvec) {
-            float4 t = ldg4(xr);
-            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-        } else {
+    // 4 rows per iteration: the neighbour index, the gathered X piece and the dY piece of all four are
+    // in flight together (the loop is latency bound on idx -> X dependent loads otherwise)
+    for (int rb = r0 + rg; rb < r1; rb += 64) {
+        int idx[4];
+        float xv[4][4], yv[4][4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) xv[a] = (ci0 + a < Cin) ? __ldg(xr + a) : 0.f;
-        }
-        if (yvec) {
-            float4 t = ldg4(yr);
-            yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
-        } else {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) yv[b] = (co0 + b < Cout) ? __ldg(yr + b) : 0.f;
+        for (int u = 0; u < 4; ++u) {
+            int r = rb + 16 * u;
+            idx[u] = (r < r1) ? (nbr ? __ldg(nbr + (size_t)k * tbl_stride + r) : r) : -1;
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int u = 0; u < 4; ++u) {
+            int r = rb + 16 * u;
+            if (idx[u] >= 0) {
+                const float* xr = X + (size_t)idx[u] * ldx + ci0;
+                const float* yr = dY + (size_t)r * ldy + co0;
+                if (xvec) {
+                    float4 t = ldg4(xr);
+                    xv[u][0] = t.x; xv[u][1] = t.y; xv[u][2] = t.z; xv[u][3] = t.w;
+                } else {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(xv[a], yv[b], acc[a][b]);
+                    for (int a = 0; a < 4; ++a) xv[u][a] = (ci0 + a < Cin) ? __ldg(xr + a) : 0.f;
+                }
+                if (yvec) {
+                    float4 t = ldg4(yr);
+                    yv[u][0] = t.x; yv[u][1] = t.y; yv[u][2] = t.z; yv[u][3] = t.w;
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) yv[u][b] = (co0 + b < Cout) ? __ldg(yr + b) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) xv[u][a] = yv[u][a] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(xv[u][a], yv[u][b], acc[a][b]);
     }
     // reduce the 16 row-groups
     __shared__ float red[16][16][17];

@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
             int* idx_t = s_idx + (titer & 1) * n_idx;
             int* idx_next = s_idx + ((titer + 1) & 1) * n_idx;
             const int next_tile = tile + gridDim.x;
+            int pend_e[2] = {-1, -1}, pend_v[2] = {0, 0};
             // position of this thread's piece on the GEMM-K axis: kk = c*32 + 4j = tap*Cin + ci
             int tap = (4 * j) / p.Cin, ci = 4 * j - tap * p.Cin;
             for (int c = 0; c < p.n_chunks; ++c) {
@@ -294,13 +295,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[stage]))
                              : "memory");
                 TC_TS(1, c);
-                if (next_tile < n_tiles) {
-                    // spread the next tile's neighbour-index loads over this tile's chunks
-                    for (int q = 0; q < Q; ++q) {
+                // Spread the next tile's neighbour-index loads over this tile's chunks, one iteration
+                // deferred (load now, store next chunk) so the global-load latency is never waited on.
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (pend_e[q] >= 0) idx_next[pend_e[q]] = pend_v[q];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    int e = (c * Q + q) * TC_GATHERERS + gt;
+                    bool ok = (next_tile < n_tiles) && q < Q && e < n_idx;
+                    pend_e[q] = ok ? e : -1;
+                    if (ok) {
+                        int k = e >> 7, row = next_tile * TC_ROWS + (e & 127);
+                        pend_v[q] = (row < n_out) ? (p.nbr ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row) : row) : -1;
+                    }
+                }
+                if (next_tile < n_tiles)
+                    for (int q = 2; q < Q; ++q) {   // only for Cin < 16 (not used by GAPartNet)
                         int e = (c * Q + q) * TC_GATHERERS + gt;
                         if (e < n_idx) load_idx(idx_next, next_tile, e);
                     }
-                }
                 ci += TC_KCHUNK;
                 while (ci >= p.Cin) {
                     ci -= p.Cin;
@@ -311,6 +325,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                     ph ^= 1;
                 }
             }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (pend_e[q] >= 0) idx_next[pend_e[q]] = pend_v[q];
             asm volatile("bar.sync 1, %0;" ::"r"(TC_GATHERERS) : "memory");   // next index tile complete
         }
         asm volatile("cp.async.wait_all;" ::: "memory");

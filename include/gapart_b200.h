@@ -146,6 +146,74 @@ int gp_gather_rows(const float* F, int ldf, int C, const int* idx, int N, float*
 int gp_scatter_add_rows(const float* dOut, int ldo, int C, const int* idx, int N, float* dF, int ldf,
                         void* stream);
 
+/* ---- epic_ops: proposal clustering and scoring ------------------------------------------------ */
+/* epic_ops.ball_query.ball_query(points, query, batch_indices, batch_offsets, radius, num_samples,
+ * point_labels=, query_labels=) -> (indices [Q,num_samples] i32, num_points_per_query [Q] i32)
+ * (gapartnet/network/grouping_utils.py:119-128).  For query q of batch b: the first num_samples
+ * points k in [batch_offsets[b], batch_offsets[b+1]) in ascending k with |p_k - q|^2 < radius^2
+ * (strict, fp32) and point_labels[k] == query_labels[q]; unused slots are -1.
+ * pts4_ws / qry4_ws: float workspaces of 4*N / 4*Q (16-byte aligned). */
+int gp_ball_query(const float* points, int p_stride, int N, const float* query, int q_stride, int Q,
+                  const int* batch_indices, const int* batch_offsets, float radius, int num_samples,
+                  const int* point_labels, const int* query_labels, float* pts4_ws, float* qry4_ws,
+                  int* indices, int* num_points_per_query, void* stream);
+
+/* epic_ops.ccl.connected_components_labeling(offsets_flat [2V] (begin,end), edges_flat,
+ * compacted=False) -> labels [V] (gapartnet/network/grouping_utils.py:135-137): label = smallest
+ * vertex index of the component; edges are treated as undirected. */
+int gp_ccl(const int* offsets_flat, const int* edges_flat, int num_vertices, int* labels, void* stream);
+
+/* cluster_proposals (gapartnet/network/grouping_utils.py:108-140) fused: ball query + components
+ * without the [Q, cap] neighbour table; cc_labels [N] as gp_ccl, num_points_per_query optional. */
+int gp_cluster(const float* points, int p_stride, int N, const int* batch_indices,
+               const int* batch_offsets, float radius, int num_samples, const int* labels,
+               float* pts4_ws, int* cc_labels, int* num_points_per_query, void* stream);
+
+/* epic_ops.reduce.segmented_reduce(x, begin, end, mode) / segmented_maxpool(x, begin, end)
+ * (gapartnet/network/grouping_utils.py:59-70, network/model.py:360-362). mode 0 sum, 1 min, 2 max;
+ * argmax (optional, mode 2) = row index of the first maximum. Empty segments give 0 / -1. */
+int gp_segmented_reduce(const float* x, int ldx, int C, const int* begin, const int* end, int S, int mode,
+                        float* out, int* argmax, void* stream);
+
+/* epic_ops.iou.batch_instance_seg_iou(proposal_offsets, instance_labels, batch_indices,
+ * num_points_per_instance) -> ious [P, Imax] (gapartnet/network/model.py:373-378) */
+int gp_instance_iou(const int* proposal_offsets, const int* instance_labels, const int* batch_indices,
+                    const int* num_points_per_instance, int P, int Imax, float* ious, void* stream);
+
+/* epic_ops.nms.nms(ious [P,P], scores, threshold) (gapartnet/network/grouping_utils.py:244): greedy;
+ * order = proposal ids by descending score (caller sorts), keep[i] = 1 iff order[i] survives. */
+int gp_nms(const float* ious, int ld, const int* order, int P, float threshold, int* keep, void* stream);
+
+/* ---- pointnet2 (the reference's own CUDA extension `pointnet2_cuda`) ---------------------------- */
+/* Same argument order and meaning as the reference's *_kernel_launcher_fast functions
+ * (dataset/process_tools/utils/pointnet_lib/src/{ball_query,group_points,sampling,interpolate}_gpu.h,
+ * bound to Python at pointnet2_api.cpp:10-25); results are bit-identical to those kernels. */
+/* ball_query_gpu.h: new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample); caller zero-fills idx */
+int gp_pn2_ball_query(int b, int n, int m, float radius, int nsample, const float* new_xyz,
+                      const float* xyz, int* idx, void* stream);
+/* group_points_gpu.h: points (B,C,N), idx (B,npoints,nsample) -> out (B,C,npoints,nsample) */
+int gp_pn2_group_points(int b, int c, int n, int npoints, int nsample, const float* points,
+                        const int* idx, float* out, void* stream);
+int gp_pn2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float* grad_out,
+                             const int* idx, float* grad_points, void* stream);
+/* sampling_gpu.h: points (B,C,N), idx (B,M) -> out (B,C,M); grad accumulates into grad_points */
+int gp_pn2_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx,
+                         float* out, void* stream);
+int gp_pn2_gather_points_grad(int b, int c, int n, int npoints, const float* grad_out, const int* idx,
+                              float* grad_points, void* stream);
+/* sampling_gpu.h: dataset (B,N,3), temp (B,N) = 1e10 -> idxs (B,M), first sample = point 0 */
+int gp_pn2_furthest_point_sampling(int b, int n, int m, const float* dataset, float* temp, int* idxs,
+                                   void* stream);
+/* interpolate_gpu.h */
+int gp_pn2_knn(int b, int n, int m, int k, const float* unknown, const float* known, float* dist2,
+               int* idx, void* stream);
+int gp_pn2_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx,
+                    void* stream);
+int gp_pn2_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx,
+                             const float* weight, float* out, void* stream);
+int gp_pn2_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx,
+                                  const float* weight, float* grad_points, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

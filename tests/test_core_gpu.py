@@ -164,11 +164,12 @@ def test_conv_fwd_bwd_matches_oracle(cuda, kind, cin, cout):
     yo, yg = oc(xo), gc(xg)
     assert yo.features.shape == yg.features.shape
     np.testing.assert_array_equal(yg.indices.cpu().numpy(), yo.indices.numpy())
-    assert rel_err(yg.features, yo.features) < 1e-5
+    # fp32 CPU oracle vs 3xTF32 tensor-core path: both carry ~sqrt(27*Cin)*2^-22 rounding noise
+    assert rel_err(yg.features, yo.features) < 5e-5
     dy = torch.randn(yo.features.shape, generator=g)
     yo.features.backward(dy)
     yg.features.backward(dy.to(cuda))
-    assert rel_err(xg.features.grad, xo.features.grad) < 1e-5
+    assert rel_err(xg.features.grad, xo.features.grad) < 5e-5
     assert rel_err(gc.weight.grad, oc.weight.grad) < 1e-4
 
 
