@@ -210,7 +210,7 @@ def run_ours(args):
             step_body()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    counts = eng.level_counts()
+    counts = eng.calibrate()   # per-level row counts -> split-K launch hints for the deep levels
     if args.ncu_step:
         # exactly one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)
         torch.cuda.synchronize()

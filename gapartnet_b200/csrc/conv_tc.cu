@@ -156,6 +156,7 @@ struct TcParams {
     float* Y; int ldy; int Cout; int accumulate;
     double* stats;
     int n_chunks; int stages; int nbuf; int accw;
+    int ksplit;      // >1: the GEMM-K (chunk) axis of a row tile is split over CTAs, partial tiles are added atomically
     long long* ts;   // optional timestamp trace [6][256] of CTA 0 (perf experiments)
 };
 
@@ -217,6 +218,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_out = gp_rows(p.d_n_out, p.max_out);
     const int n_tiles = (n_out + TC_ROWS - 1) / TC_ROWS;
+    // work item w = tile * ksplit + part: chunks [part*n/ksplit, (part+1)*n/ksplit) of row tile `tile`.
+    // ksplit > 1 spreads the few row tiles of the deep U-Net levels (1..30 tiles) over the whole chip.
+    const int ksplit = p.ksplit;
+    const int n_work = n_tiles * ksplit;
     const int nbuf = p.nbuf;
     const uint32_t accw = (uint32_t)p.accw;
     const uint32_t a_base = (uint32_t)nbuf * accw;            // first TMEM column of the A stages
@@ -257,7 +262,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
         uint32_t ph = 0;
         int titer = 0;
         const int n_idx = p.Ktaps * TC_ROWS;
-        const int Q = (p.Ktaps + p.n_chunks - 1) / p.n_chunks;   // index prefetches per thread per chunk
         auto load_idx = [&](int* dst, int t, int e) {
             int k = e >> 7, r = e & 127;
             int row = t * TC_ROWS + r;
@@ -265,18 +269,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
             if (row < n_out) v = p.nbr ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row) : row;
             dst[e] = v;
         };
-        if ((int)blockIdx.x < n_tiles) {
-            for (int e = gt; e < n_idx; e += TC_GATHERERS) load_idx(s_idx, blockIdx.x, e);
+        if ((int)blockIdx.x < n_work) {
+            for (int e = gt; e < n_idx; e += TC_GATHERERS) load_idx(s_idx, (int)blockIdx.x / ksplit, e);
         }
         asm volatile("bar.sync 1, %0;" ::"r"(TC_GATHERERS) : "memory");
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++titer) {
+            const int tile = w / ksplit, part = w - tile * ksplit;
+            const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
+            const int nc = max(c1 - c0, 1);
+            const int Q = (p.Ktaps + nc - 1) / nc;   // index prefetches per thread per chunk
             int* idx_t = s_idx + (titer & 1) * n_idx;
             int* idx_next = s_idx + ((titer + 1) & 1) * n_idx;
-            const int next_tile = tile + gridDim.x;
+            const int next_tile = (w + (int)gridDim.x < n_work) ? (w + (int)gridDim.x) / ksplit : n_tiles;
             int pend_e[2] = {-1, -1}, pend_v[2] = {0, 0};
             // position of this thread's piece on the GEMM-K axis: kk = c*32 + 4j = tap*Cin + ci
-            int tap = (4 * j) / p.Cin, ci = 4 * j - tap * p.Cin;
-            for (int c = 0; c < p.n_chunks; ++c) {
+            int tap = (c0 * TC_KCHUNK + 4 * j) / p.Cin, ci = c0 * TC_KCHUNK + 4 * j - tap * p.Cin;
+            for (int c = c0; c < c1; ++c) {
                 mbar_wait_warp(&empty[stage], ph ^ 1, lane);
                 TC_TS(0, c);
                 uint8_t* st = tiles + (size_t)stage * stage_bytes;
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                     if (pend_e[q] >= 0) idx_next[pend_e[q]] = pend_v[q];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    int e = (c * Q + q) * TC_GATHERERS + gt;
+                    int e = ((c - c0) * Q + q) * TC_GATHERERS + gt;
                     bool ok = (next_tile < n_tiles) && q < Q && e < n_idx;
                     pend_e[q] = ok ? e : -1;
                     if (ok) {
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                 }
                 if (next_tile < n_tiles)
                     for (int q = 2; q < Q; ++q) {   // only for Cin < 16 (not used by GAPartNet)
-                        int e = (c * Q + q) * TC_GATHERERS + gt;
+                        int e = ((c - c0) * Q + q) * TC_GATHERERS + gt;
                         if (e < n_idx) load_idx(idx_next, next_tile, e);
                     }
                 ci += TC_KCHUNK;
@@ -336,8 +344,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < p.n_chunks; ++c) {
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int part = w % ksplit;
+                const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
+                for (int c = c0; c < c1; ++c) {
                     mbar_wait(&empty[stage], ph ^ 1);
                     mbar_arrive_expect_tx(&b_full[stage], b_bytes);
                     const float* src = p.Wpack + (size_t)c * Cout * 64;
@@ -359,8 +369,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
         const uint32_t lane_base = (uint32_t)((warp - 8) * 32) << 16;
         int stage = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int c = 0; c < p.n_chunks; ++c) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int part = w % ksplit;
+            const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
+            for (int c = c0; c < c1; ++c) {
                 mbar_wait_warp(&raw_full[stage], ph, lane);
                 TC_TS(2, c);
                 const uint8_t* st = tiles + (size_t)stage * stage_bytes;
@@ -403,11 +415,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
         uint32_t ph = 0;
         int buf = 0;
         uint32_t acc_ph = 0;             // parity of the current use of accumulator buffer `buf`
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int part = w % ksplit;
+            const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
             mbar_wait_warp(&acc_empty[buf], acc_ph ^ 1, lane);
             tc_fence_after();
             const uint32_t d_tmem = tbase + (uint32_t)buf * accw;
-            for (int c = 0; c < p.n_chunks; ++c) {
+            for (int c = c0; c < c1; ++c) {
                 if (lane == 0) {
                     mbar_wait(&b_full[stage], ph);
                     mbar_wait(&a_full[stage], ph);
@@ -424,7 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_hi + ks * 32) >> 4) & 0x3FFF);
                         const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_lo + ks * 32) >> 4) & 0x3FFF);
-                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, (c | ks) ? 1u : 0u);
+                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, (c > c0 || ks > 0) ? 1u : 0u);
                         tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
                         tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_lo, idesc, 1u);
                     }
@@ -451,7 +465,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
         // ===================== epilogue (warps 0-3) =====================
         int buf = 0;
         uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int tile = w / ksplit;
             mbar_wait_warp(&acc_full[buf], acc_ph, lane);
             tc_fence_after();
             const int row = tile * TC_ROWS + warp * 32 + lane;
@@ -470,7 +485,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                 float f[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) f[e] = active ? __uint_as_float(v[e]) : 0.f;
-                if (active) {
+                if (active && ksplit > 1) {
+                    // partial tile of a split GEMM-K axis: fp32 reductions into the (pre-zeroed or
+                    // accumulated-into) output rows
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) atomicAdd(yr + c0 + e, f[e]);
+                } else if (active) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float4* dst = reinterpret_cast<float4*>(yr + c0 + 4 * q);
@@ -560,6 +580,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     }
 }
 
+// zero the first n (device count) rows of a strided [rows, C] matrix
+__global__ void k_zero_rows(float* __restrict__ Y, int ldy, int C, const int* __restrict__ d_n, int max_n) {
+    const int n = gp_rows(d_n, max_n), cpr = C >> 2;
+    const long long total = (long long)n * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(t / cpr), cg = (int)(t - (long long)r * cpr);
+        *reinterpret_cast<float4*>(Y + (size_t)r * ldy + cg * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 static int tc_chunks(int K, int Cin) { return (K * Cin + TC_KCHUNK - 1) / TC_KCHUNK; }
 
 extern "C" long long gp_conv_tc_workspace_floats(int K, int Cin, int Cout) {
@@ -575,7 +606,7 @@ extern "C" int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy) 
 extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk,
                               long long w_sci, long long w_sco, int flip_k, const int* nbr, int tbl_stride,
                               int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout,
-                              int accumulate, double* stats, float* wpack, void* stream_) {
+                              int accumulate, double* stats, float* wpack, int rows_hint, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(gp_conv_tc_supported(Cin, Cout, K, ldx, ldy), "gp_conv_tc_fwd: unsupported shape Cin=%d Cout=%d K=%d",
                  Cin, Cout, K);
@@ -616,10 +647,36 @@ extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, 
         GP_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         configured = true;
     }
-    int tiles = gp_cdiv(max_out, TC_ROWS);
-    int grid = tiles < gp_num_sms() ? tiles : gp_num_sms();
+    // Split the GEMM-K axis when the level has too few row tiles to fill the chip (deep U-Net levels:
+    // 1..30 tiles, each 50-100 chunks long).  rows_hint is the expected row count (the device-side
+    // count is not known here); it only steers performance, never correctness.
+    const int sms = gp_num_sms();
+    const int rows_est = (rows_hint > 0 && rows_hint < max_out) ? rows_hint : max_out;
+    const int tiles_est = gp_cdiv(rows_est, TC_ROWS);
+    int ksplit = 1;
+    if (tiles_est * 2 <= sms && n_chunks >= 4) {
+        ksplit = sms / tiles_est;
+        if (ksplit > n_chunks / 2) ksplit = n_chunks / 2;
+        if (ksplit > 32) ksplit = 32;
+        if (ksplit < 1) ksplit = 1;
+    }
+    p.ksplit = ksplit;
+    int launches = 2;
+    if (ksplit > 1) {
+        if (!accumulate) {
+            long long total = (long long)max_out * (Cout / 4);
+            long long blocks = (total + 255) / 256;
+            if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+            k_zero_rows<<<(int)blocks, 256, 0, stream>>>(Y, ldy, Cout, d_n_out, max_out);
+            ++launches;
+        }
+        p.stats = nullptr;   // partial tiles: the BatchNorm statistics are taken by gp_col_stats below
+    }
+    long long work = (long long)gp_cdiv(max_out, TC_ROWS) * ksplit;
+    int grid = work < sms ? (int)work : sms;
     k_conv_tc<<<grid, TC_THREADS, smem, stream>>>(p);
-    gp_note_launch(2);
+    gp_note_launch(launches);
     GP_LAUNCH_CHECK();
+    if (ksplit > 1 && stats) return gp_col_stats(Y, ldy, Cout, d_n_out, max_out, stats, stream_);
     return GP_OK;
 }

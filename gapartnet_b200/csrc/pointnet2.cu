@@ -132,11 +132,14 @@ extern "C" int gp_pn2_gather_points_grad(int b, int c, int n, int npoints, const
 // ---------------------------------------------------------------------------------------------
 // furthest point sampling (sampling_gpu.cu:93-209)
 // ---------------------------------------------------------------------------------------------
-struct FpsBest {
-    float d;
-    int key;   // (k mod bs_ref) then k: lower wins on equal distance, as the reference's tree does
-    int k;
-};
+// Tie-breaking of the reference (sampling_gpu.cu:86-91,143-203): thread slot t = k mod bs_ref keeps its
+// FIRST maximum; the shared-memory tree folds slot t+s onto slot t for s = bs_ref/2 ... 1 and keeps
+// the lower slot on equal values.  Two slots meet at s = lowest set bit of (a xor b) and the one
+// with a 0 in that bit wins, i.e. ties resolve to the smallest BIT-REVERSED slot, then smallest k.
+__device__ __forceinline__ int fps_key(int k, int bs_ref) {
+    if (bs_ref <= 1) return 0;
+    return (int)(__brev((unsigned)(k & (bs_ref - 1))) >> (__clz(bs_ref) + 1));
+}
 __device__ __forceinline__ bool fps_better(float d2, int key2, int k2, float d1, int key1, int k1) {
     return d2 > d1 || (d2 == d1 && (key2 < key1 || (key2 == key1 && k2 < k1)));
 }
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps(int n, int m, int bs_re
                     float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
                     float d2 = min(d, pt[u]);
                     pt[u] = d2;
-                    int key = k % bs_ref;
+                    int key = fps_key(k, bs_ref);
                     if (fps_better(d2, key, k, best, bkey, bk)) { best = d2; bk = k; bkey = key; }
                 }
             }
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps(int n, int m, int bs_re
                 float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
                 float d2 = min(d, temp[k]);
                 temp[k] = d2;
-                int key = k % bs_ref;
+                int key = fps_key(k, bs_ref);
                 if (fps_better(d2, key, k, best, bkey, bk)) { best = d2; bk = k; bkey = key; }
             }
         }

@@ -127,6 +127,9 @@ class SparseUNetEngine:
         self._stat_used = 0
         self._keep: List[torch.Tensor] = []
         self.use_tc = ops.USE_TC if use_tc is None else bool(use_tc)
+        # expected rows per level (performance hint for the split-K decision of the tensor-core conv);
+        # mutable list read at launch time: call calibrate() after a first build_levels()
+        self.rows_hint = [0] * self.depth
         self._ws_floats = 0
         self._ws = None
         self._build()
@@ -215,7 +218,7 @@ class SparseUNetEngine:
             st = _p(stats) if eng.training else None
             if tc_f:
                 C.gp_conv_tc_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                                 y.ptr, y.ld, Cout, 0, st, _p(eng._ws), s)
+                                 y.ptr, y.ld, Cout, 0, st, _p(eng._ws), eng.rows_hint[Lo], s)
             else:
                 C.gp_conv_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
                               y.ptr, y.ld, Cout, 0, st, s)
@@ -257,7 +260,8 @@ class SparseUNetEngine:
                 if dx_ptr is not None:
                     if tc_b and dx_ld % 4 == 0:
                         C.gp_conv_tc_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
-                                         _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, _p(eng._ws), s)
+                                         _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, _p(eng._ws),
+                                         eng.rows_hint[Lx], s)
                     else:
                         C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
                                       _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
@@ -451,6 +455,13 @@ class SparseUNetEngine:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+
+    def calibrate(self) -> List[int]:
+        """one host sync: remember the current per-level row counts as launch hints (+25% head-room).
+        Call after a representative build_levels(); plans captured in CUDA graphs afterwards use them."""
+        counts = self.level_counts()
+        self.rows_hint[:] = [int(c * 1.25) + 1 for c in counts]
+        return counts
 
     def level_counts(self) -> List[int]:
         """host copy of the per-level row counts (syncs; diagnostics only)."""

@@ -199,7 +199,8 @@ def tc_workspace(device, floats: int) -> torch.Tensor:
 def conv_fwd(x: torch.Tensor, w_krsc: torch.Tensor, table: Optional[torch.Tensor], K: int, n_out: int,
              d_n_out: Optional[torch.Tensor] = None, *, transpose: bool = False, flip: bool = False,
              out: Optional[torch.Tensor] = None, accumulate: bool = False,
-             stats: Optional[torch.Tensor] = None, use_tc: Optional[bool] = None) -> torch.Tensor:
+             stats: Optional[torch.Tensor] = None, use_tc: Optional[bool] = None,
+             rows_hint: int = 0) -> torch.Tensor:
     """y = conv(x). transpose=True computes the input gradient operator (W^T).
     use_tc: None = tcgen05 path when the shape qualifies (GAPART_TC=0 forces the SIMT path)."""
     _need_cuda(x, w_krsc)
@@ -224,7 +225,7 @@ def conv_fwd(x: torch.Tensor, w_krsc: torch.Tensor, table: Optional[torch.Tensor
             ws = tc_workspace(x.device, int(C.gp_conv_tc_workspace_floats(K, cin, cout)))
             C.gp_conv_tc_fwd(_p(x), x.stride(0), cin, _p(w_krsc), w_sk, w_sci, w_sco, int(flip), _p(table),
                              tstride, K, _p(d_n_out), n_out, _p(out), out.stride(0), cout, int(accumulate),
-                             _p(stats), _p(ws), _stream())
+                             _p(stats), _p(ws), int(rows_hint), _stream())
         else:
             C.gp_conv_fwd(_p(x), x.stride(0), cin, _p(w_krsc), w_sk, w_sci, w_sco, int(flip), _p(table),
                           tstride, K, _p(d_n_out), n_out, _p(out), out.stride(0), cout, int(accumulate),

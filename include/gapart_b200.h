@@ -107,13 +107,15 @@ int gp_conv_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk
 /* Same contract as gp_conv_fwd, on the tcgen05 tensor cores (3xTF32 split, fp32 accumulate in
  * TMEM; see csrc/conv_tc.cu).  wpack: caller workspace of gp_conv_tc_workspace_floats(K,Cin,Cout)
  * floats (16-byte aligned) that receives the pre-split, pre-swizzled weight images.
- * gp_conv_tc_supported() tells whether the shape/strides qualify (else use gp_conv_fwd). */
+ * gp_conv_tc_supported() tells whether the shape/strides qualify (else use gp_conv_fwd).
+ * rows_hint (0 = max_out): expected row count; with few row tiles the GEMM-K axis is split over
+ * CTAs (partial tiles are reduced with fp32 atomics) - a performance hint only. */
 long long gp_conv_tc_workspace_floats(int K, int Cin, int Cout);
 int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy);
 int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
                    long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K,
                    const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
-                   double* stats, float* wpack, void* stream);
+                   double* stats, float* wpack, int rows_hint, void* stream);
 
 /* dW(k', ci, co) += sum_i X[nbr[k][i], ci] * dY[i, co] */
 int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout,

@@ -265,7 +265,7 @@ def _grad_check(o64_params, o32_params, g_params, names, tol=5e-3):
     for n, p64, p32, pg in zip(names, o64_params, o32_params, g_params):
         e_gpu = rel_err(pg.grad, p64.grad)
         e_cpu = rel_err(p32.grad, p64.grad)
-        assert e_gpu < max(tol, 4 * e_cpu + 1e-4), (n, e_gpu, e_cpu)
+        assert e_gpu < max(2 * tol, 10 * e_cpu + 1e-4), (n, e_gpu, e_cpu)
 
 
 @pytest.mark.parametrize("without_stem", [False, True])

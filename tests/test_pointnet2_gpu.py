@@ -95,7 +95,7 @@ def test_knn_three_nn_interpolate(cuda, ref, corc):
     d, idx = pu.knn(k, t(unk), t(kn))
     cd, cidx = corc.knn(k, unk, kn)
     np.testing.assert_array_equal(idx.cpu().numpy(), cidx)
-    np.testing.assert_array_equal((d * d).cpu().numpy().round(6), cd.round(6))
+    np.testing.assert_allclose(d.cpu().numpy(), np.sqrt(cd), rtol=2e-6, atol=1e-7)   # wrapper returns sqrt(dist2)
     d3, i3 = pu.three_nn(t(unk), t(kn))
     c3d, c3i = corc.knn(3, unk, kn)
     np.testing.assert_array_equal(i3.cpu().numpy(), c3i)
@@ -103,7 +103,9 @@ def test_knn_three_nn_interpolate(cuda, ref, corc):
     w = g.uniform(0, 1, size=(b, n, 3)).astype(np.float32)
     f = t(feats).requires_grad_(True)
     out = pu.three_interpolate(f, i3, t(w))
-    np.testing.assert_array_equal(out.detach().cpu().numpy(), corc.three_interpolate(feats, c3i, w))
+    # the C restatement guesses nvcc's FMA contraction of w0*p0 + w1*p1 + w2*p2: 1-ulp differences are
+    # possible, bit-exactness is asserted against the reference's own kernel below
+    np.testing.assert_allclose(out.detach().cpu().numpy(), corc.three_interpolate(feats, c3i, w), rtol=1e-5, atol=1e-6)
     go = torch.randn_like(out)
     out.backward(go)
     ref_grad = torch.zeros(b, c, m, device=cuda)
@@ -113,7 +115,7 @@ def test_knn_three_nn_interpolate(cuda, ref, corc):
     if ref is not None:
         rd, ri = torch.empty(b, n, k, device=cuda), torch.zeros(b, n, k, dtype=torch.int32, device=cuda)
         ref("knn", b, n, m, k, t(unk), t(kn), rd, ri)
-        assert torch.equal(idx, ri) and torch.equal(d * d, rd) or torch.allclose(d * d, rd, rtol=1e-6)
+        assert torch.equal(idx, ri) and torch.equal(d, torch.sqrt(rd))
         rd3, ri3 = torch.empty(b, n, 3, device=cuda), torch.zeros(b, n, 3, dtype=torch.int32, device=cuda)
         ref("three_nn", b, n, m, t(unk), t(kn), rd3, ri3)
         assert torch.equal(i3, ri3)
