@@ -75,18 +75,22 @@ __global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ Y, 
             q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
         }
     }
-    extern __shared__ double sm[];  // [2][C]
-    for (int i = threadIdx.x; i < 2 * C; i += 256) sm[i] = 0.0;
-    __syncthreads();
+    // per-row-lane fp32 partials -> smem, then 2C threads fold them in fp64 (no shared-memory double
+    // atomics: those are CAS loops and cost 30 us per call under 64-way contention)
+    extern __shared__ float part[];  // [rpb][2C]
     if (rl < rpb) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            atomicAdd(&sm[cg * 4 + j], (double)s[j]);
-            atomicAdd(&sm[C + cg * 4 + j], (double)q[j]);
+            part[rl * 2 * C + cg * 4 + j] = s[j];
+            part[rl * 2 * C + C + cg * 4 + j] = q[j];
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(stats + i, sm[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        double acc = 0.0;
+        for (int r = 0; r < rpb; ++r) acc += (double)part[r * 2 * C + i];
+        atomicAdd(stats + i, acc);
+    }
 }
 
 extern "C" int gp_col_stats(const float* Y, int ldy, int C, const int* d_n, int max_n, double* stats,
@@ -95,7 +99,7 @@ extern "C" int gp_col_stats(const float* Y, int ldy, int C, const int* d_n, int 
     GP_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024 && ldy % 4 == 0, "gp_col_stats: C must be a multiple of 4");
     if (max_n == 0) return GP_OK;
     int rows_per_block = 512;
-    k_col_stats<<<gp_cdiv(max_n, rows_per_block), 256, 2 * C * sizeof(double), stream>>>(
+    k_col_stats<<<gp_cdiv(max_n, rows_per_block), 256, (size_t)(256 / (C / 4)) * 2 * C * sizeof(float), stream>>>(
         Y, ldy, C, d_n, max_n, stats, rows_per_block);
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
@@ -189,18 +193,22 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
             q[2] += g.z * (y.z - mu.z) * is.z; q[3] += g.w * (y.w - mu.w) * is.w;
         }
     }
-    extern __shared__ double sm[];
-    for (int i = threadIdx.x; i < 2 * C; i += 256) sm[i] = 0.0;
-    __syncthreads();
+    // per-row-lane fp32 partials -> smem, then 2C threads fold them in fp64 (no shared-memory double
+    // atomics: those are CAS loops and cost 30 us per call under 64-way contention)
+    extern __shared__ float part[];  // [rpb][2C]
     if (rl < rpb) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            atomicAdd(&sm[cg * 4 + j], (double)s[j]);
-            atomicAdd(&sm[C + cg * 4 + j], (double)q[j]);
+            part[rl * 2 * C + cg * 4 + j] = s[j];
+            part[rl * 2 * C + C + cg * 4 + j] = q[j];
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(sums + i, sm[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        double acc = 0.0;
+        for (int r = 0; r < rpb; ++r) acc += (double)part[r * 2 * C + i];
+        atomicAdd(sums + i, acc);
+    }
 }
 
 // backward pass 2: dY = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); optional dRes (+)= dz;
@@ -273,7 +281,7 @@ extern "C" int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const
     if (max_n == 0) return GP_OK;
     if (zero_sums) GP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), stream));
     int rows_per_block = 512;
-    k_bn_bwd_reduce<<<gp_cdiv(max_n, rows_per_block), 256, 2 * C * sizeof(double), stream>>>(
+    k_bn_bwd_reduce<<<gp_cdiv(max_n, rows_per_block), 256, (size_t)(256 / (C / 4)) * 2 * C * sizeof(float), stream>>>(
         dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, sums, rows_per_block);
     k_bn_bwd_apply<<<ew_grid((long long)max_n * (C / 4)), 256, 0, stream>>>(
         dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, sums, dY, lddy, dRes, ldres,
