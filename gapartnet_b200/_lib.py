@@ -109,7 +109,7 @@ class _Caller:
         lib = load()
         fn = getattr(lib, name)
         ret = _protos[name][0]
-        if ret == "int" and name not in ("gp_version", "gp_device_sms", "gp_conv_tc_supported"):
+        if ret == "int" and name not in ("gp_version", "gp_device_sms", "gp_conv_tc_supported", "gp_conv_wgrad_tc_supported"):
             def call(*args, _fn=fn, _name=name):
                 rc = _fn(*args)
                 if rc != 0:

@@ -69,10 +69,19 @@ __global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ Y, 
     int cg = threadIdx.x % cpr, rl = threadIdx.x / cpr;
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     if (rl < rpb) {
-        for (int r = r0 + rl; r < r1; r += rpb) {
-            float4 v = ldg4(Y + (size_t)r * ldy + cg * 4);
-            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-            q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+        // 4 rows per iteration: independent 16-byte loads in flight (the loop is latency bound otherwise)
+        for (int rb = r0 + rl; rb < r1; rb += 4 * rpb) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = rb + u * rpb;
+                v[u] = r < r1 ? ldg4(Y + (size_t)r * ldy + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+                q[0] += v[u].x * v[u].x; q[1] += v[u].y * v[u].y; q[2] += v[u].z * v[u].z; q[3] += v[u].w * v[u].w;
+            }
         }
     }
     // per-row-lane fp32 partials -> smem, then 2C threads fold them in fp64 (no shared-memory double
@@ -178,19 +187,27 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     if (rl < rpb) {
         float4 mu = ldg4(mean + cg * 4), is = ldg4(invstd + cg * 4);
-        for (int r = r0 + rl; r < r1; r += rpb) {
-            float4 g = ldg4(dA + (size_t)r * lda + cg * 4);
-            if (A) {
-                float4 a = ldg4(A + (size_t)r * la + cg * 4);
-                if (!(a.x > 0.f)) g.x = 0.f;
-                if (!(a.y > 0.f)) g.y = 0.f;
-                if (!(a.z > 0.f)) g.z = 0.f;
-                if (!(a.w > 0.f)) g.w = 0.f;
+        // 4 rows per iteration: 12 independent 16-byte loads in flight per thread
+        for (int rb = r0 + rl; rb < r1; rb += 4 * rpb) {
+            float4 g[4], a[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = rb + u * rpb;
+                const bool ok = r < r1;
+                g[u] = ok ? ldg4(dA + (size_t)r * lda + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                a[u] = (ok && A) ? ldg4(A + (size_t)r * la + cg * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                y[u] = ok ? ldg4(Y + (size_t)r * ldy + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            float4 y = ldg4(Y + (size_t)r * ldy + cg * 4);
-            s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
-            q[0] += g.x * (y.x - mu.x) * is.x; q[1] += g.y * (y.y - mu.y) * is.y;
-            q[2] += g.z * (y.z - mu.z) * is.z; q[3] += g.w * (y.w - mu.w) * is.w;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!(a[u].x > 0.f)) g[u].x = 0.f;
+                if (!(a[u].y > 0.f)) g[u].y = 0.f;
+                if (!(a[u].z > 0.f)) g[u].z = 0.f;
+                if (!(a[u].w > 0.f)) g[u].w = 0.f;
+                s[0] += g[u].x; s[1] += g[u].y; s[2] += g[u].z; s[3] += g[u].w;
+                q[0] += g[u].x * (y[u].x - mu.x) * is.x; q[1] += g[u].y * (y[u].y - mu.y) * is.y;
+                q[2] += g[u].z * (y[u].z - mu.z) * is.z; q[3] += g[u].w * (y[u].w - mu.w) * is.w;
+            }
         }
     }
     // per-row-lane fp32 partials -> smem, then 2C threads fold them in fp64 (no shared-memory double

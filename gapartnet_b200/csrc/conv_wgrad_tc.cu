@@ -1,0 +1,308 @@
+// Weight gradients of the sparse convolutions on the tcgen05 tensor cores (sm_100a).
+//
+//   dW[co][(tap,ci)]  +=  sum_rows  X[nbr[tap][row]][ci] * dY[row][co]
+//
+// as the GEMM  D[M = 128 (tap,ci) values (TMEM lanes)][N = Cout] += A[M][K = rows] * B[K][N]:
+//   A = X_g^T : K-major operand in TENSOR MEMORY (lane = (tap,ci), column = row).  The gather writes the
+//               same [64 rows][32 floats] 128B-swizzled tiles as conv_tc.cu; the transpose is free: the
+//               convert thread that owns TMEM lane n reads column n of the tile (a warp reads one
+//               contiguous 128-byte row per LDS - conflict free), splits hi/lo and issues tcgen05.st.
+//               No transposed copy is ever stored in shared memory.
+//   B = dY^T  : small K-major smem tile [Cout][64 rows] (hi | lo), written by the convert warps.
+//   D         : fp32 in TMEM; lane m holds dW[:, m]: the epilogue's reductions into the KRSC weight
+//               gradient [Cout][K][Cin] are coalesced across lanes.
+// (An MN-major TF32 smem operand - which would let the tensor core read the gather tile directly -
+//  returned zeros on B200 in our experiments, so both operands are K-major like the forward kernel.)
+// One CTA owns one 128-wide slice ("pass") of the (tap,ci) axis and a strided subset of the 64-row
+// tiles; partial slices are combined with fp32 red.global.  3xTF32: D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
+//
+// Warp roles (416 threads, 1 CTA/SM): 4 epilogue | 4 gather (cp.async, zero-fill, noinc barrier) |
+// 4 convert (X^T -> TMEM, dY^T -> smem) | 1 MMA issuer (elected lane, uniform operands).
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+#include "../../include/gapart_b200.h"
+
+#define WG_ROWS 64                    // rows (GEMM-K) per tile: 8 MMA K-steps
+#define WG_NCH 4                      // 32-float chunks per pass: M = 128 lanes
+#define WG_XTILE (WG_ROWS * 128)      // bytes of one chunk tile (64 rows x 128 B)
+#define WG_XBYTES (WG_NCH * WG_XTILE) // raw gathered X of one stage = 32 KB
+#define WG_THREADS 416
+#define WG_TMEM_COLS 512
+
+struct WgParams {
+    const float* X; int ldx; int Cin;
+    const float* dY; int ldy; int Cout;
+    const int* nbr; int tbl_stride; int Ktaps;
+    const int* d_n_out; int max_out;
+    float* dW; long long w_sco;       // KRSC: dW[co * w_sco + tap * Cin + ci]
+    int n_chunks; int passes; int row_groups; int stages;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int S = p.stages;
+    const uint32_t b_tile = (uint32_t)p.Cout * 128;             // one K-chunk (32 rows) of dY^T: [Cout][32 floats]
+    const uint32_t b_bytes = 4 * b_tile;                        // hi: 2 K-chunks, lo: 2 K-chunks
+    const uint32_t stage_bytes = WG_XBYTES + b_bytes;
+    uint8_t* tiles = smem;                                      // [S][X raw 32 KB | dY^T hi | dY^T lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)S * stage_bytes);
+    uint64_t* empty = bars;                    // [S] MMA finished with the stage (smem B + TMEM A)
+    uint64_t* raw_full = bars + S;             // [S] gathered X rows landed
+    uint64_t* ab_full = bars + 2 * S;          // [S] X^T hi/lo in TMEM and dY^T hi/lo in smem ready
+    uint64_t* acc_full = bars + 3 * S;         // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_out = gp_rows(p.d_n_out, p.max_out);
+    const int n_rt = (n_out + WG_ROWS - 1) / WG_ROWS;
+    const int pass = blockIdx.x % p.passes, rg = blockIdx.x / p.passes;
+    const int c_first = pass * WG_NCH;
+    const int nch = min(WG_NCH, p.n_chunks - c_first);          // chunks of this pass (>= 1)
+    const int my_tiles = rg < n_rt ? (n_rt - 1 - rg) / p.row_groups + 1 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&empty[s], 1);
+            mbar_init(&raw_full[s], 128);
+            mbar_init(&ab_full[s], 4);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)WG_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: D [0,128) (Cout <= 128 used) | A stage s at 128 + 128*s: hi [0,64) lo [64,128)
+
+    if (my_tiles > 0) {
+        if (warp >= 4 && warp < 8) {
+            // ===================== gather X rows of the pass's chunks =====================
+            const int gt = tid - 128;
+            const int j = gt & 7, cc = (gt >> 3) & 3, rq = gt >> 5;      // piece, chunk in pass, row quarter
+            const int kk = (c_first + cc) * 32 + 4 * j;                   // GEMM-M index of this piece
+            const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
+            const bool col_ok = cc < nch && tap < p.Ktaps;
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int row0 = (rg + t * p.row_groups) * WG_ROWS;
+                mbar_wait_warp(&empty[stage], ph ^ 1, lane);
+                uint8_t* st = tiles + (size_t)stage * stage_bytes + cc * WG_XTILE;
+                int idx[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int row = row0 + rq + 4 * i;
+                    idx[i] = -1;
+                    if (col_ok && row < n_out) idx[i] = p.nbr ? __ldg(p.nbr + (size_t)tap * p.tbl_stride + row) : row;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float* src = p.X + (idx[i] >= 0 ? ((size_t)idx[i] * p.ldx + ci) : 0);
+                    uint32_t nbytes = idx[i] >= 0 ? 16u : 0u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                                     smem_u32(st + swz128(rq + 4 * i, j))),
+                                 "l"(src), "r"(nbytes));
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[stage]))
+                             : "memory");
+                if (++stage == S) { stage = 0; ph ^= 1; }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        } else if (warp >= 8 && warp < 12) {
+            // ===================== convert: X^T -> TMEM (hi|lo), dY^T -> smem (hi|lo) =====================
+            const int n = tid - 256;                  // TMEM lane = (tap,ci) column of this pass
+            const int cc = n >> 5, col = n & 31;      // a warp = one chunk tile, lanes = its 32 columns
+            const uint32_t lane_base = (uint32_t)((warp - 8) * 32) << 16;
+            const int n_b = WG_ROWS * p.Cout;         // elements of the dY tile
+            const int r_first = n / p.Cout, co_first = n - r_first * p.Cout;
+            const int step_r = 128 / p.Cout, step_co = 128 - step_r * p.Cout;
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int row0 = (rg + t * p.row_groups) * WG_ROWS;
+                uint8_t* st = tiles + (size_t)stage * stage_bytes;
+                // raw_full fires only after the gather passed `empty` for this round, so the stage's
+                // smem B tiles and TMEM A columns are free to overwrite from here on
+                mbar_wait_warp(&raw_full[stage], ph, lane);
+                uint8_t* bh = st + WG_XBYTES;
+                {
+                    // element e = n + 128*i of the [64][Cout] dY tile; (r, co) advance without division and
+                    // 8 global loads are in flight before the first dependent store
+                    int r = r_first, co = co_first;
+                    for (int base = n; base < n_b; base += 128 * 8) {
+                        float v[8];
+                        uint32_t off[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const bool ok = base + 128 * u < n_b;
+                            const int row = row0 + r;
+                            v[u] = (ok && row < n_out) ? __ldg(p.dY + (size_t)row * p.ldy + co) : 0.f;
+                            off[u] = ok ? ((uint32_t)(r >> 5) * b_tile + swz128(co, (r & 31) >> 2) + (r & 3) * 4)
+                                        : 0xFFFFFFFFu;
+                            co += step_co;
+                            r += step_r;
+                            if (co >= p.Cout) { co -= p.Cout; ++r; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (off[u] != 0xFFFFFFFFu) {
+                                const float h = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
+                                *reinterpret_cast<float*>(bh + off[u]) = h;
+                                *reinterpret_cast<float*>(bh + 2 * b_tile + off[u]) = v[u] - h;
+                            }
+                        }
+                    }
+                }
+                const uint32_t a_stage = tmem_base + lane_base + 128u + 128u * (uint32_t)stage;
+                const uint8_t* xt = st + cc * WG_XTILE + (col & 3) * 4;
+                const int pj = col >> 2;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float v[32], h[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                        v[r] = cc < nch ? *reinterpret_cast<const float*>(xt + swz128(half * 32 + r, pj)) : 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) h[r] = __uint_as_float(__float_as_uint(v[r]) & 0xffffe000u);
+                    tmem_st32(a_stage + half * 32, h);
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] -= h[r];
+                    tmem_st32(a_stage + 64 + half * 32, v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // dY^T smem writes -> tensor core
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ab_full[stage]);
+                if (++stage == S) { stage = 0; ph ^= 1; }
+            }
+        } else if (warp == 12) {
+            // ===================== MMA issuer =====================
+            // A: TF32 K-major (TMEM), B: TF32 K-major (smem, 128B swizzle), D: F32, M = 128, N = Cout
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+            const uint32_t tbase = uniform(tmem_base);
+            const uint32_t tiles_u32 = uniform(smem_u32(tiles));
+            const uint32_t bars_u32 = uniform(smem_u32(bars));
+            const uint32_t desc_hi = (uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                mbar_wait_warp(&ab_full[stage], ph, lane);
+                tc_fence_after();
+                const uint32_t b_hi = tiles_u32 + (uint32_t)stage * stage_bytes + WG_XBYTES;
+                const uint32_t b_lo = b_hi + 2 * b_tile;
+                const uint32_t a_hi = tbase + 128u + 128u * (uint32_t)stage;
+                const uint32_t empty_bar = bars_u32 + (uint32_t)stage * 8;
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t koff = (uint32_t)(ks >> 2) * b_tile + (uint32_t)(ks & 3) * 32;
+                        const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_hi + koff) >> 4) & 0x3FFF);
+                        const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_lo + koff) >> 4) & 0x3FFF);
+                        tc_mma_tf32_ts(tbase, a_hi + ks * 8, db_hi, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+                        tc_mma_tf32_ts(tbase, a_hi + 64 + ks * 8, db_hi, idesc, 1u);
+                        tc_mma_tf32_ts(tbase, a_hi + ks * 8, db_lo, idesc, 1u);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     empty_bar)
+                                 : "memory");
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; ph ^= 1; }
+            }
+            if (elect_one()) tc_commit(acc_full);
+            __syncwarp();
+        } else {
+            // ===================== epilogue: D[lane m][co] -> dW[co][m] (coalesced fp32 reductions) ==========
+            mbar_wait_warp(acc_full, 0, lane);
+            tc_fence_after();
+            const int m = c_first * 32 + warp * 32 + lane;
+            const bool m_ok = (warp < nch) && m < p.Ktaps * p.Cin;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                if (m_ok) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float f = __uint_as_float(v[e]);
+                        if (f != 0.f) atomicAdd(p.dW + (size_t)(c0 + e) * p.w_sco + m, f);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 12) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)WG_TMEM_COLS));
+    }
+}
+
+// 1 if the tensor-core wgrad supports the shape / layout (KRSC weights), else use gp_conv_wgrad
+extern "C" int gp_conv_wgrad_tc_supported(int Cin, int Cout, int K, int ldx, int ldy, long long w_sk,
+                                          long long w_sci) {
+    return (Cin % 4 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 128 && K >= 1 && K <= 27 && (ldx % 4 == 0) &&
+           w_sci == 1 && w_sk == Cin;
+}
+
+extern "C" int gp_conv_wgrad_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout,
+                                const int* nbr, int tbl_stride, int K, const int* d_n_out, int max_out,
+                                float* dW, long long w_sk, long long w_sci, long long w_sco, int rows_hint,
+                                void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(gp_conv_wgrad_tc_supported(Cin, Cout, K, ldx, ldy, w_sk, w_sci),
+                 "gp_conv_wgrad_tc: unsupported shape/layout Cin=%d Cout=%d K=%d", Cin, Cout, K);
+    GP_CHECK_ARG((reinterpret_cast<size_t>(X) & 15) == 0, "gp_conv_wgrad_tc: X must be 16-byte aligned");
+    GP_CHECK_ARG(nbr != nullptr || K == 1, "gp_conv_wgrad_tc: identity table needs K == 1");
+    if (max_out == 0) return GP_OK;
+    WgParams p;
+    p.X = X; p.ldx = ldx; p.Cin = Cin; p.dY = dY; p.ldy = ldy; p.Cout = Cout; p.nbr = nbr; p.tbl_stride = tbl_stride;
+    p.Ktaps = K; p.d_n_out = d_n_out; p.max_out = max_out; p.dW = dW; p.w_sco = w_sco;
+    p.n_chunks = (K * Cin + 31) / 32;
+    p.passes = (p.n_chunks + WG_NCH - 1) / WG_NCH;
+    const int sms = gp_num_sms();
+    const int rows_est = (rows_hint > 0 && rows_hint < max_out) ? rows_hint : max_out;
+    const int n_rt_est = gp_cdiv(rows_est, WG_ROWS);
+    int rgs = sms / p.passes;
+    if (rgs < 1) rgs = 1;
+    if (rgs > n_rt_est) rgs = n_rt_est;
+    p.row_groups = rgs;
+    const size_t stage_bytes = WG_XBYTES + (size_t)Cout * 512;
+    const size_t budget = 227 * 1024, fixed = 1024 + 512;
+    int S = (int)((budget - fixed) / stage_bytes);
+    if (S > 3) S = 3;               // TMEM: D 128 columns + 3 x 128 A columns
+    GP_CHECK_ARG(S >= 2, "gp_conv_wgrad_tc: not enough shared memory for Cout=%d", Cout);
+    p.stages = S;
+    const size_t smem = fixed + (size_t)S * stage_bytes;
+    static thread_local bool configured = false;
+    if (!configured) {
+        GP_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        configured = true;
+    }
+    k_wgrad_tc<<<p.passes * rgs, WG_THREADS, smem, stream>>>(p);
+    gp_note_launch(1);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}

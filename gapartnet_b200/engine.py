@@ -209,6 +209,7 @@ class SparseUNetEngine:
 
         tc_f = eng.use_tc and bool(C.gp_conv_tc_supported(Cin, Cout, K, x.ld, y.ld))
         tc_b = eng.use_tc and bool(C.gp_conv_tc_supported(Cout, Cin, K, y.ld, x.ld))
+        tc_w = eng.use_tc and x.ptr % 16 == 0 and bool(C.gp_conv_wgrad_tc_supported(Cin, Cout, K, x.ld, y.ld, Cin, 1))
         if tc_f or tc_b:
             eng._ws_floats = max(eng._ws_floats, int(C.gp_conv_tc_workspace_floats(K, Cin, Cout)),
                                  int(C.gp_conv_tc_workspace_floats(K, Cout, Cin)))
@@ -265,8 +266,12 @@ class SparseUNetEngine:
                     else:
                         C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
                                       _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
-                C.gp_conv_wgrad(x.ptr, x.ld, Cin, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                                wg_ptr, Cin, 1, K * Cin, 0, s)
+                if tc_w:
+                    C.gp_conv_wgrad_tc(x.ptr, x.ld, Cin, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
+                                       wg_ptr, Cin, 1, K * Cin, eng.rows_hint[Lo], s)
+                else:
+                    C.gp_conv_wgrad(x.ptr, x.ld, Cin, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
+                                    wg_ptr, Cin, 1, K * Cin, 0, s)
 
             return bwd, n_launch
 

@@ -234,15 +234,23 @@ def conv_fwd(x: torch.Tensor, w_krsc: torch.Tensor, table: Optional[torch.Tensor
 
 
 def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, dw_krsc: torch.Tensor, table: Optional[torch.Tensor],
-               K: int, n_out: int, d_n_out: Optional[torch.Tensor] = None) -> None:
-    """dw_krsc += sum_i x[table[k][i]]^T dy[i]"""
+               K: int, n_out: int, d_n_out: Optional[torch.Tensor] = None, *, use_tc: Optional[bool] = None,
+               rows_hint: int = 0) -> None:
+    """dw_krsc += sum_i x[table[k][i]]^T dy[i]   (tcgen05 path when the shape qualifies)"""
     _need_cuda(x, dy, dw_krsc)
     Cout_w, Cin_w = dw_krsc.shape[0], dw_krsc.shape[-1]
     assert dw_krsc.is_contiguous() and x.shape[1] == Cin_w and dy.shape[1] == Cout_w
     tstride = table.shape[1] if table is not None else 0
     if n_out > 0:
-        C.gp_conv_wgrad(_p(x), x.stride(0), Cin_w, _p(dy), dy.stride(0), Cout_w, _p(table), tstride, K,
-                        _p(d_n_out), n_out, _p(dw_krsc), Cin_w, 1, K * Cin_w, 0, _stream())
+        tc = USE_TC if use_tc is None else use_tc
+        tc = tc and x.data_ptr() % 16 == 0 and bool(
+            C.gp_conv_wgrad_tc_supported(Cin_w, Cout_w, K, x.stride(0), dy.stride(0), Cin_w, 1))
+        if tc:
+            C.gp_conv_wgrad_tc(_p(x), x.stride(0), Cin_w, _p(dy), dy.stride(0), Cout_w, _p(table), tstride, K,
+                               _p(d_n_out), n_out, _p(dw_krsc), Cin_w, 1, K * Cin_w, int(rows_hint), _stream())
+        else:
+            C.gp_conv_wgrad(_p(x), x.stride(0), Cin_w, _p(dy), dy.stride(0), Cout_w, _p(table), tstride, K,
+                            _p(d_n_out), n_out, _p(dw_krsc), Cin_w, 1, K * Cin_w, 0, _stream())
 
 
 def gather_rows(f: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:

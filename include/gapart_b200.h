@@ -122,6 +122,13 @@ int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, in
                   const int* nbr, int tbl_stride, int K, const int* d_n_out, int max_out, float* dW,
                   long long w_sk, long long w_sci, long long w_sco, int flip_k, void* stream);
 
+/* gp_conv_wgrad on the tcgen05 tensor cores (3xTF32; csrc/conv_wgrad_tc.cu). Needs KRSC weight strides
+ * (w_sci == 1, w_sk == Cin), Cin % 4 == 0, Cout <= 128; rows_hint as in gp_conv_tc_fwd. */
+int gp_conv_wgrad_tc_supported(int Cin, int Cout, int K, int ldx, int ldy, long long w_sk, long long w_sci);
+int gp_conv_wgrad_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, const int* nbr,
+                     int tbl_stride, int K, const int* d_n_out, int max_out, float* dW, long long w_sk,
+                     long long w_sci, long long w_sco, int rows_hint, void* stream);
+
 /* ---- BatchNorm1d(eps=1e-4, momentum=0.1) in training mode + ReLU + residual ------------------- */
 /* (norm_fn gapartnet/network/model.py:86; ResBlock.forward gapartnet/network/backbone.py:40-49) */
 int gp_col_stats(const float* Y, int ldy, int C, const int* d_n, int max_n, double* stats,

@@ -119,3 +119,57 @@ def test_tc_many_tiles_persistent(cuda):
     w = (torch.randn(16, 27, 16, generator=g) * 0.1).to(cuda)
     y = ops.conv_fwd(x, w, nbr, 27, M, use_tc=True)
     assert rel_err(y, _ref(x, w, nbr, 27, M)) < 2e-5
+
+
+WG_SHAPES = [(16, 16), (32, 16), (16, 32), (32, 32), (48, 48), (64, 64), (112, 112), (224, 112), (64, 32)]
+
+
+@pytest.mark.parametrize("cin,cout", WG_SHAPES)
+def test_tc_wgrad_matches_fp64(cuda, cin, cout):
+    """tcgen05 weight gradient (dY^T in TMEM x gathered X as MN-major smem operand) vs fp64 and vs SIMT"""
+    t = _table(cuda)
+    M = t["M"]
+    g = torch.Generator(device="cpu").manual_seed(7 * cin + cout)
+    x = torch.randn(M, cin, generator=g).to(cuda)
+    dy = torch.randn(M, cout, generator=g).to(cuda)
+    dw_tc = torch.zeros(cout, 27, cin, device=cuda)
+    dw_si = torch.zeros_like(dw_tc)
+    ops.conv_wgrad(x, dy, dw_tc, t["nbr"], 27, M, use_tc=True)
+    ops.conv_wgrad(x, dy, dw_si, t["nbr"], 27, M, use_tc=False)
+    ref = torch.zeros(cout, 27, cin, dtype=torch.float64, device=cuda)
+    for k in range(27):
+        idx = t["nbr"][k].long()
+        ok = idx >= 0
+        ref[:, k, :] = dy[ok].double().t() @ x[idx[ok]].double()
+    assert rel_err(dw_si, ref) < 1e-5
+    assert rel_err(dw_tc, ref) < 2e-5
+
+
+@pytest.mark.parametrize("kind,n_rows", [("down", None), ("up", None), ("k1", None), ("subm", 1), ("subm", 65), ("subm", 1000)])
+def test_tc_wgrad_tables_device_count_strided_accumulate(cuda, kind, n_rows):
+    t = _table(cuda, n=3000)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    M, Mo = t["M"], t["Mo"]
+    if kind == "down":
+        xin, tbl, K, nout, cin, cout = torch.randn(M, 32, generator=g), t["child"], 8, Mo, 32, 48
+    elif kind == "up":
+        xin, tbl, K, nout, cin, cout = torch.randn(Mo, 48, generator=g), t["parent8"], 8, M, 48, 32
+    elif kind == "k1":
+        xin, tbl, K, nout, cin, cout = torch.randn(M, 64, generator=g), None, 1, M, 64, 32
+    else:
+        xin, tbl, K, nout, cin, cout = torch.randn(M, 64, generator=g), t["nbr"], 27, M, 32, 16
+    xin = xin.to(cuda)
+    x = xin[:, 32:] if kind == "subm" else xin            # strided view for the subm case (ld 64, C 32)
+    dycat = torch.randn(nout, 48, generator=g).to(cuda)
+    dy = dycat[:, 16:16 + cout] if cout <= 32 else torch.randn(nout, cout, generator=g).to(cuda)
+    n = nout if n_rows is None else n_rows
+    d_n = torch.tensor([n], dtype=torch.int32, device=cuda)
+    dw0 = torch.randn(cout, K, cin, generator=g).to(cuda)
+    dw = dw0.clone()
+    ops.conv_wgrad(x, dy, dw, tbl, K, nout, d_n, use_tc=True)
+    ref = dw0.double()
+    for k in range(K):
+        idx = tbl[k, :n].long() if tbl is not None else torch.arange(n, device=cuda)
+        ok = idx >= 0
+        ref[:, k, :] += dy[:n][ok].double().t() @ x[idx[ok]].double()
+    assert rel_err(dw, ref) < 2e-5
