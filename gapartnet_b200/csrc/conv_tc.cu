@@ -3,41 +3,67 @@
 //   D[128 rows x Cout] (TMEM, fp32)  +=  A[128 x (taps*Cin)] (gathered rows)  x  B[(taps*Cin) x Cout]
 //
 // Output-stationary like the SIMT path (conv_simt.cu): one CTA owns 128 consecutive output rows, the
-// GEMM-K axis runs over (tap, ci) in chunks of 32 floats (= one 128-byte swizzle row), so any
-// Cin that is a multiple of 4 packs densely (Cin=16: two taps per chunk).  Absent neighbours are
-// zero-filled by cp.async (src-size 0): they cost no HBM/L2 traffic, only idle MMA lanes - which is
-// why the tensor pipe is used here at all: the contraction is ~50 flop/B, 5x over the fp32 FFMA
-// ridge, and FFMA made the U-Net compute bound (profiles/).
+// GEMM-K axis runs over (tap, ci) in chunks of 32 floats, so any Cin that is a multiple of 4 packs
+// densely (Cin=16: two taps per chunk).  Why tensor cores at all: the contraction is ~50 flop/B, 5x
+// over the fp32 FFMA ridge, and FFMA made the U-Net compute bound (profiles/).
 //
 // fp32 parity (north_star: logits within 1e-3 rel after ~100 conv+BN layers) rules out plain TF32
 // (10-bit mantissa).  We use the 3xTF32 split: a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits),
 //   D += a_hi*b_hi + a_lo*b_hi + a_hi*b_lo          (error ~2^-21, fp32 accumulate in TMEM)
 //
-// Warp roles (448 threads, 1 CTA/SM, persistent over 128-row tiles), see k_conv_tc:
-//   epilogue x4 | gather x4 (cp.async, zero-fill) | convert x4 (hi/lo split -> TMEM A operand) |
-//   MMA issuer x1 (tcgen05.mma kind::tf32, A from TMEM, B from smem) | weight loader x1 (TMA bulk)
-// Weights are pre-split and pre-swizzled into per-chunk smem images by k_pack_weights.
-// Pipelines: per-stage mbarriers empty -> raw_full/b_full -> a_full -> (commit) empty, and
-// full/empty per TMEM accumulator buffer (double buffered: the epilogue overlaps the next tile).
-// Measured lessons kept in the code: mbarrier hops cost ~400 cycles, so every role runs ahead on
-// its own (stage, phase) counters; integer division and lane-divergent MMA issue (R2UR waterfall)
-// each cost >1k cycles per chunk and are gone; GAPART_TC_TS=<device ptr> records a clock64 trace.
+// Data path of the A operand (third design; measurements in profiles/r1_summary.md, tests/micro/):
+//   v1/v2  cp.async(16 B, zero-fill) -> swizzled smem tile -> convert warps (LDS, split) -> TMEM.
+//          An SM sustains only ~1 LDGSTS.128 per 30 cycles (850-1400 cycles per 16 KB chunk with 4-16
+//          gather warps, independent of how many lanes actually fetch), TMA tile::gather4 ~135 cycles per
+//          instruction and warp: both far below the L2 rate.
+//   v3     (this file) "feeder" warps gather straight into REGISTERS with coalesced LDG.128 - four lanes
+//          own one row, each lane fetches one 16-byte piece of the left and of the right 64-byte half of
+//          the chunk row (170-400 cycles per chunk in the same micro-benchmark) - split hi/lo in place
+//          and store both operands to tensor memory with tcgen05.st.16x256b, whose register<->(lane,
+//          column) map is exactly "4 lanes per row" (tests/micro/tmem_layout.cu).  No shared-memory
+//          staging, no LDS, no data barrier between gather and convert; absent neighbours are zeros in
+//          registers.  The price is a fixed permutation of the 32 K positions inside a chunk, which
+//          k_pack_weights applies to the weight images (tc_kperm).
+//
+// Warp roles (704 threads, 1 CTA/SM, persistent over work items = (128-row tile, K split part)):
+//   warps 0-3    epilogue : tcgen05.ld accumulator -> global rows (+BN sum/sumsq), double-buffered TMEM
+//   warps 4-19   feeders  : 4 groups x 4 TMEM quadrants; group g feeds chunks n == g (mod 4) into A stage g
+//   warp  20     MMA      : elected lane issues 12 tcgen05.mma.kind::tf32 per chunk (A from TMEM, B smem)
+//   warp  21     loader   : weight images (cp.async.bulk per chunk) + neighbour-index tiles of the next
+//                           work item (Ktaps bulk copies), completion on mbarriers
+// Lessons kept from v1/v2: mbarrier hops cost ~400 cycles (every role runs ahead on its own counters);
+// a bare try_wait loop burnt 58 % of all issued instructions (nanosleep back-off in mbar_wait);
+// 64-bit division and lane-divergent MMA issue (R2UR waterfall) each cost >1k cycles per chunk;
+// GAPART_TC_TS=<device ptr> records a clock64 trace of CTA 0.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
 #include "../../include/gapart_b200.h"
 
 #define TC_ROWS 128
-#define TC_KCHUNK 32                      // floats per chunk = 128 bytes
-#define TC_A_TILE (TC_ROWS * 128)         // bytes of one A tile (hi or lo)
-#define TC_PRODUCERS 256
-#define TC_THREADS 448
+#define TC_KCHUNK 32                      // floats per chunk
+#define TC_GROUPS 2                       // feeder groups; TMEM A stages = TC_GROUPS * spg (1 or 2 per group)
+#define TC_FEED_WARPS (4 * TC_GROUPS)
+#define TC_WARP_MMA (4 + TC_FEED_WARPS)
+#define TC_WARP_LOAD (TC_WARP_MMA + 1)
+#define TC_THREADS (32 * (TC_WARP_LOAD + 1))
 #define TC_MAX_TAPS 27
+#define TC_TMEM_COLS 512
 
-#define TC_TS(ev, g) do { if (p.ts && blockIdx.x == 0 && lane == 0 && (tid == 160 || tid == 256 || tid == 384) && (g) < 256) p.ts[(ev) * 256 + (g)] = clock64(); } while (0)
+// trace slot = sequence number of the chunk within CTA 0 (quadrant-1 warp of every feeder group + the MMA warp)
+#define TC_TS(ev, g) do { if (p.ts && blockIdx.x == 0 && lane == 0 && (g) < 256) p.ts[(ev) * 256 + (g)] = clock64(); } while (0)
+
+// K position `col` (0..31) of a chunk's TMEM operand holds source float tc_kperm(col) of the chunk:
+// tcgen05.st.16x256b puts registers {4n+2h+e} of thread (g, q) at lane g+8h, column 8n+2q+e; a feeder thread
+// holds floats 4q..4q+3 of the left 16-float half (n = 0,1) and of the right half (n = 2,3) of its rows.
+__host__ __device__ __forceinline__ int tc_kperm(int col) {
+    const int n = col >> 3, q = (col >> 1) & 3, e = col & 1;
+    return ((n & 2) ? 16 : 0) + 4 * q + 2 * (n & 1) + e;
+}
+
 // ---------------------------------------------------------------------------------------------
 // weights -> per-chunk smem images: chunk c = [hi: Cout x 32 floats swizzled][lo: same]
-// B(n, kk) = W(tap', ci, co=n), kk = tap*Cin + ci, tap' = flip ? Ktaps-1-tap : tap
+// B(n, col) = W(tap', ci, co=n), c*32 + tc_kperm(col) = tap*Cin + ci, tap' = flip ? Ktaps-1-tap : tap
 // ---------------------------------------------------------------------------------------------
 __global__ void k_pack_weights(const float* __restrict__ W, long long w_sk, long long w_sci, long long w_sco,
                                int flip_k, int Ktaps, int Cin, int Cout, int n_chunks,
@@ -51,7 +77,7 @@ __global__ void k_pack_weights(const float* __restrict__ W, long long w_sk, long
     float hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        int kk = c * TC_KCHUNK + j * 4 + e;
+        int kk = c * TC_KCHUNK + tc_kperm(j * 4 + e);
         int tap = kk / Cin, ci = kk - tap * Cin;
         float w = 0.f;
         if (tap < Ktaps) {
@@ -76,41 +102,39 @@ struct TcParams {
     const int* d_n_out; int max_out;
     float* Y; int ldy; int Cout; int accumulate;
     double* stats;
-    int n_chunks; int stages; int nbuf; int accw;
+    int n_chunks; int nbuf; int accw; int spg;
     int ksplit;      // >1: the GEMM-K (chunk) axis of a row tile is split over CTAs, partial tiles are added atomically
+    int idx_bulk;    // 1: a tile's neighbour indices arrive as Ktaps cp.async.bulk copies (16-byte aligned table)
+    uint32_t inv_cin;  // floor(2^32 / Cin) + 1: kk / Cin == umulhi(kk, inv_cin) for kk < 2^16
     long long* ts;   // optional timestamp trace [6][256] of CTA 0 (perf experiments)
 };
 
-#define TC_TMEM_COLS 512
-#define TC_GATHERERS 128
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
 
-// Warp roles (416 threads, 1 CTA/SM, persistent over 128-row tiles):
-//   warps 0-3   epilogue : tcgen05.ld accumulator -> (+= old) -> global rows, BN sum/sumsq
-//   warps 4-7   gather   : cp.async (16 B, zero-fill for absent neighbours) of raw fp32 rows into a
-//                          128B-swizzled smem tile; completion is signalled by the copies themselves
-//                          (cp.async.mbarrier.arrive.noinc) so these threads never wait on data
-//   warps 8-11  convert  : thread = row = TMEM lane: 8 conflict-free LDS.128 of its row, hi/lo split,
-//                          two tcgen05.st into the A operand region of tensor memory
-//   warp  12    MMA      : one thread issues tcgen05.mma.kind::tf32 with A from TMEM, B (weights)
-//                          from smem; 12 MMAs per 32-wide K chunk (3xTF32)
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int Cout = p.Cout;
     const uint32_t b_bytes = (uint32_t)Cout * 256;            // hi + lo weight image of one chunk
-    const uint32_t stage_bytes = TC_A_TILE + b_bytes;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* tiles = smem;
-    int* s_idx = reinterpret_cast<int*>(tiles + (size_t)p.stages * stage_bytes);          // [2][Ktaps][128]
-    double* s_stats = reinterpret_cast<double*>(s_idx + 2 * p.Ktaps * TC_ROWS);           // [2][Cout]
+    uint8_t* tiles = smem;                                                                 // [SB] weight images
+    const int SB = TC_GROUPS * p.spg;
+    int* s_idx = reinterpret_cast<int*>(tiles + (size_t)SB * b_bytes);                     // [2][Ktaps][128]
+    double* s_stats = reinterpret_cast<double*>(s_idx + 2 * p.Ktaps * TC_ROWS);            // [2][Cout]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + 2 * Cout);
-    const int S = p.stages;
-    uint64_t* empty = bars;                 // [S]  MMA done with smem stage + TMEM A stage
-    uint64_t* raw_full = bars + S;          // [S]  gathered rows landed in smem
-    uint64_t* b_full = bars + 2 * S;        // [S]  weight image landed in smem
-    uint64_t* a_full = bars + 3 * S;        // [S]  hi/lo operand written to TMEM
-    uint64_t* acc_full = bars + 4 * S;      // [2]
-    uint64_t* acc_empty = acc_full + 2;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int SA = TC_GROUPS * p.spg;             // ring depth of both operands: TMEM A stages and weight images
+    uint64_t* st_free = bars;                     // [SA]  MMAs that read stage s (TMEM A + smem B) retired
+    uint64_t* st_full = st_free + SA;             // [SA]  4 feeder warps wrote A hi/lo + the weight image landed
+    uint64_t* acc_full = st_full + SA;            // [2]
+    uint64_t* acc_empty = acc_full + 2;           // [2]
+    uint64_t* idx_full = acc_empty + 2;           // [2]   neighbour-index tile of a work item landed
+    uint64_t* idx_empty = idx_full + 2;           // [2]   every feeder warp is done with the index tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(idx_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_out = gp_rows(p.d_n_out, p.max_out);
@@ -122,22 +146,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     const int nbuf = p.nbuf;
     const uint32_t accw = (uint32_t)p.accw;
     const uint32_t a_base = (uint32_t)nbuf * accw;            // first TMEM column of the A stages
+    const bool use_tbl = p.nbr != nullptr;
+    const int n_idx = p.Ktaps * TC_ROWS;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&empty[s], 1);
-            mbar_init(&raw_full[s], TC_GATHERERS);   // noinc arrive of every gather thread
-            mbar_init(&b_full[s], 1);
-            mbar_init(&a_full[s], 4);
+        for (int s = 0; s < SA; ++s) {
+            mbar_init(&st_free[s], 1);
+            mbar_init(&st_full[s], 5);      // 4 feeder warps + the loader's expect_tx arrive
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], 4);
+            mbar_init(&idx_full[b], 1);
+            mbar_init(&idx_empty[b], TC_FEED_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 2 * Cout; i += TC_THREADS) s_stats[i] = 0.0;
-    if (warp == 12) {
+    if (warp == TC_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -147,157 +173,238 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
-        // ===================== gather: global -> smem (raw fp32, swizzled) =====================
-        // Fully decoupled from consumption: the copies themselves arm raw_full (noinc arrive), so
-        // these warps run up to S chunks ahead and never wait on data.  No integer division in the
-        // loop: (stage, phase) and (tap, ci) advance incrementally.
-        const int gt = tid - 128;
-        const int j = gt & 7;            // 16-byte piece within the 128-byte chunk row
-        const int r0 = gt >> 3;          // rows r0 + 16*i
+    if (warp >= 4 && warp < TC_WARP_MMA) {
+        // ===================== feeders: global -> registers -> hi/lo -> TMEM =====================
+        // Group `grp` feeds the chunks with sequence number n == grp (mod G) of this CTA (the sequence runs on
+        // across work items) into A stage n % (G * spg).  The gather of the group's NEXT chunk is issued before
+        // the current one is converted (two register sets), so the L2 latency is hidden behind convert + MMA.
+        const int fw = warp - 4, grp = fw >> 2, quad = fw & 3;     // quad == warp % 4 == this warp's TMEM quadrant
+        const int g = lane >> 2, q = lane & 3;
+        // TMEM lane 32*quad + 16*sub + 8*h + g (register slot s = 2*sub + h of thread (g, q)) holds tile row
+        // 32*quad + 4*g + s: a thread's 4 rows are consecutive, so their 4 neighbour indices of a tap are ONE
+        // 16-byte shared-memory load; the epilogue applies the same lane -> row map.
+        const int rloc0 = 32 * quad + 4 * g;
+        const char* Xb = reinterpret_cast<const char*>(p.X);
+        const uint32_t ld_bytes = (uint32_t)p.ldx * 4u;
+        const uint32_t t_quad = tmem_base + ((uint32_t)(32 * quad) << 16) + a_base;
+        const int spg = p.spg;
+
+        struct Cur { int w, titer, c, c1, row0; uint32_t idx_a; bool valid, full; };
+        // enter work item (w, titer) at chunk offset `over` from its first chunk; skips items the group has no
+        // chunk in (their index tile is still released: every feeder warp arrives once per work item)
+        auto enter = [&](Cur& k, int over) {
+            while (true) {
+                if (k.w >= n_work) { k.valid = false; return; }
+                const int tile = k.w / ksplit, part = k.w - tile * ksplit;
+                const int c0 = (part * p.n_chunks) / ksplit;
+                k.c1 = ((part + 1) * p.n_chunks) / ksplit;
+                k.c = c0 + over;
+                if (k.c < k.c1) {
+                    k.row0 = tile * TC_ROWS + rloc0;
+                    k.full = (tile + 1) * TC_ROWS <= n_out;
+                    k.idx_a = smem_u32(s_idx + (k.titer & 1) * n_idx + rloc0);
+                    if (use_tbl) mbar_wait_warp(&idx_full[k.titer & 1], (k.titer >> 1) & 1, lane);
+                    k.valid = true;
+                    return;
+                }
+                over = k.c - k.c1;
+                if (use_tbl) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&idx_empty[k.titer & 1]);
+                }
+                k.w += gridDim.x;
+                ++k.titer;
+            }
+        };
+        auto advance = [&](Cur& k) {
+            k.c += TC_GROUPS;
+            if (k.c < k.c1) return;
+            const int over = k.c - k.c1;
+            if (use_tbl) {   // all index reads of this work item are done (their LDG consumers were issued)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&idx_empty[k.titer & 1]);
+            }
+            k.w += gridDim.x;
+            ++k.titer;
+            enter(k, over);
+        };
+        const bool ragged_k = (p.Ktaps * p.Cin) % TC_KCHUNK != 0;   // last chunk reaches past the last tap
+        auto gather = [&](const Cur& k, float4* vL, float4* vR) {
+            // K position of the thread's left / right piece: kk = tap*Cin + ci
+            const uint32_t kkL = (uint32_t)k.c * TC_KCHUNK + 4u * q, kkR = kkL + 16u;
+            uint32_t tapL = __umulhi(kkL, p.inv_cin), tapR = __umulhi(kkR, p.inv_cin);
+            const char* XL = Xb + (kkL - tapL * (uint32_t)p.Cin) * 4u;
+            const char* XR = Xb + (kkR - tapR * (uint32_t)p.Cin) * 4u;
+            int iL[4], iR[4];
+            const bool edge = !k.full || (ragged_k && k.c == p.n_chunks - 1);   // warp-uniform
+            if (!edge) {
+                if (use_tbl) {
+                    lds_i32x4(k.idx_a + tapL * (TC_ROWS * 4u), iL);
+                    lds_i32x4(k.idx_a + tapR * (TC_ROWS * 4u), iR);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) iL[s] = iR[s] = k.row0 + s;
+                }
+            } else {
+                const bool okL = tapL < (uint32_t)p.Ktaps, okR = tapR < (uint32_t)p.Ktaps;
+                if (!okL) tapL = 0;
+                if (!okR) tapR = 0;
+                if (use_tbl) {
+                    lds_i32x4(k.idx_a + tapL * (TC_ROWS * 4u), iL);
+                    lds_i32x4(k.idx_a + tapR * (TC_ROWS * 4u), iR);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) iL[s] = iR[s] = k.row0 + s;
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const bool row_ok = k.row0 + s < n_out;
+                    if (!row_ok || !okL) iL[s] = -1;
+                    if (!row_ok || !okR) iR[s] = -1;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                vL[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                vR[s] = vL[s];
+                if (iL[s] >= 0) vL[s] = ldg4(reinterpret_cast<const float*>(XL + (uint64_t)(uint32_t)iL[s] * ld_bytes));
+                if (iR[s] >= 0) vR[s] = ldg4(reinterpret_cast<const float*>(XR + (uint64_t)(uint32_t)iR[s] * ld_bytes));
+            }
+        };
+        uint32_t use = 0;          // chunks this group has fed so far
+        auto feed = [&](const float4* vL, const float4* vR) {
+            const int tn = (int)use * TC_GROUPS + grp;   // sequence number of the chunk (trace only)
+            const uint32_t slot = use & (uint32_t)(spg - 1), round = use >> (spg - 1);   // spg is 1 or 2
+            const uint32_t sa = (uint32_t)grp + TC_GROUPS * slot;
+            if (quad == 1) TC_TS(0, tn);
+            // the TMEM stage is free once the MMAs of the chunk that used it last retired
+            mbar_wait_warp(&st_free[sa], (round & 1) ^ 1, lane);
+            tc_fence_after();
+            if (quad == 1) TC_TS(1, tn);
+            const uint32_t t_stage = t_quad + sa * 64u;
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                float v[16], h[16];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const float4 l = vL[2 * sub + hh], r = vR[2 * sub + hh];
+                    v[0 + 2 * hh] = l.x; v[1 + 2 * hh] = l.y; v[4 + 2 * hh] = l.z; v[5 + 2 * hh] = l.w;
+                    v[8 + 2 * hh] = r.x; v[9 + 2 * hh] = r.y; v[12 + 2 * hh] = r.z; v[13 + 2 * hh] = r.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) h[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+                const uint32_t ta = t_stage + ((uint32_t)(16 * sub) << 16);
+                tmem_st_16x256b_x4(ta, h);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] -= h[e];
+                tmem_st_16x256b_x4(ta + 32, v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st_full[sa]);
+            if (quad == 1) TC_TS(3, tn);
+            ++use;
+        };
+
+        Cur k;
+        k.w = blockIdx.x; k.titer = 0; k.c = 0; k.c1 = 0; k.row0 = 0; k.idx_a = 0; k.valid = false;
+        enter(k, grp);
+        float4 aL[4], aR[4], bL[4], bR[4];
+        if (k.valid) {
+            gather(k, aL, aR);
+            while (true) {
+                advance(k);
+                bool more = k.valid;
+                if (more) gather(k, bL, bR);
+                feed(aL, aR);
+                if (!more) break;
+                advance(k);
+                more = k.valid;
+                if (more) gather(k, aL, aR);
+                feed(bL, bR);
+                if (!more) break;
+            }
+        }
+    } else if (warp == TC_WARP_LOAD) {
+        // ===================== loader: weight images (one TMA bulk copy per chunk) and the
+        // neighbour-index tile of the NEXT work item (Ktaps bulk copies of 512 B) =====================
         int stage = 0;
         uint32_t ph = 0;
         int titer = 0;
-        const int n_idx = p.Ktaps * TC_ROWS;
-        auto load_idx = [&](int* dst, int t, int e) {
-            int k = e >> 7, r = e & 127;
-            int row = t * TC_ROWS + r;
-            int v = -1;
-            if (row < n_out) v = p.nbr ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row) : row;
-            dst[e] = v;
-        };
-        if ((int)blockIdx.x < n_work) {
-            for (int e = gt; e < n_idx; e += TC_GATHERERS) load_idx(s_idx, (int)blockIdx.x / ksplit, e);
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(TC_GATHERERS) : "memory");
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++titer) {
-            const int tile = w / ksplit, part = w - tile * ksplit;
-            const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
-            const int nc = max(c1 - c0, 1);
-            const int Q = (p.Ktaps + nc - 1) / nc;   // index prefetches per thread per chunk
-            int* idx_t = s_idx + (titer & 1) * n_idx;
-            int* idx_next = s_idx + ((titer + 1) & 1) * n_idx;
-            const int next_tile = (w + (int)gridDim.x < n_work) ? (w + (int)gridDim.x) / ksplit : n_tiles;
-            int pend_e[2] = {-1, -1}, pend_v[2] = {0, 0};
-            // position of this thread's piece on the GEMM-K axis: kk = c*32 + 4j = tap*Cin + ci
-            int tap = (c0 * TC_KCHUNK + 4 * j) / p.Cin, ci = c0 * TC_KCHUNK + 4 * j - tap * p.Cin;
-            for (int c = c0; c < c1; ++c) {
-                mbar_wait_warp(&empty[stage], ph ^ 1, lane);
-                TC_TS(0, c);
-                uint8_t* st = tiles + (size_t)stage * stage_bytes;
-                const bool tap_ok = tap < p.Ktaps;
-                int idx[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) idx[i] = tap_ok ? idx_t[tap * TC_ROWS + r0 + 16 * i] : -1;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float* src = p.X + (idx[i] >= 0 ? ((size_t)idx[i] * p.ldx + ci) : 0);
-                    uint32_t nbytes = idx[i] >= 0 ? 16u : 0u;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                                     smem_u32(st + swz128(r0 + 16 * i, j))),
-                                 "l"(src), "r"(nbytes));
-                }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[stage]))
-                             : "memory");
-                TC_TS(1, c);
-                // Spread the next tile's neighbour-index loads over this tile's chunks, one iteration
-                // deferred (load now, store next chunk) so the global-load latency is never waited on.
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-                    if (pend_e[q] >= 0) idx_next[pend_e[q]] = pend_v[q];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    int e = ((c - c0) * Q + q) * TC_GATHERERS + gt;
-                    bool ok = (next_tile < n_tiles) && q < Q && e < n_idx;
-                    pend_e[q] = ok ? e : -1;
-                    if (ok) {
-                        int k = e >> 7, row = next_tile * TC_ROWS + (e & 127);
-                        pend_v[q] = (row < n_out) ? (p.nbr ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row) : row) : -1;
+        // index tile of work item w (the t-th of this CTA) into buffer t&1.  Its previous user (work item
+        // t-2) must have released it; `try_only` polls instead of blocking so that the weight pipeline of the
+        // current work item is never held up by the prefetch.  Returns true once issued.
+        auto load_idx_tile = [&](int w, int t, bool try_only) -> bool {
+            const int b = t & 1;
+            int* dst = s_idx + b * n_idx;
+            const int row0 = (w / ksplit) * TC_ROWS;
+            int rows = p.tbl_stride - row0;
+            rows = rows < TC_ROWS ? rows : TC_ROWS;
+            if (p.idx_bulk) {
+                if (lane == 0) {   // only lane 0 runs the loader in this mode
+                    if (t >= 2) {
+                        const uint32_t par = ((t >> 1) & 1) ^ 1;
+                        if (try_only) {
+                            if (!mbar_test(&idx_empty[b], par)) return false;
+                        } else {
+                            mbar_wait(&idx_empty[b], par);
+                        }
+                    }
+                    const uint32_t bytes = (uint32_t)rows * 4u;
+                    mbar_arrive_expect_tx(&idx_full[b], bytes * (uint32_t)p.Ktaps);
+                    for (int k = 0; k < p.Ktaps; ++k) {
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(dst + k * TC_ROWS)),
+                            "l"(p.nbr + (size_t)k * p.tbl_stride + row0), "r"(bytes), "r"(smem_u32(&idx_full[b]))
+                            : "memory");
                     }
                 }
-                if (next_tile < n_tiles)
-                    for (int q = 2; q < Q; ++q) {   // only for Cin < 16 (not used by GAPartNet)
-                        int e = ((c - c0) * Q + q) * TC_GATHERERS + gt;
-                        if (e < n_idx) load_idx(idx_next, next_tile, e);
-                    }
-                ci += TC_KCHUNK;
-                while (ci >= p.Cin) {
-                    ci -= p.Cin;
-                    ++tap;
-                }
-                if (++stage == S) {
-                    stage = 0;
-                    ph ^= 1;
-                }
+                return true;
             }
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-                if (pend_e[q] >= 0) idx_next[pend_e[q]] = pend_v[q];
-            asm volatile("bar.sync 1, %0;" ::"r"(TC_GATHERERS) : "memory");   // next index tile complete
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp == 13) {
-        // ===================== weight loader: one TMA bulk copy per chunk =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t ph = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            // unaligned table (compat path): plain loads by the whole warp, blocking
+            if (try_only) return false;
+            if (t >= 2) mbar_wait_warp(&idx_empty[b], ((t >> 1) & 1) ^ 1, lane);
+            for (int e = lane; e < n_idx; e += 32) {
+                const int k = e >> 7, r = e & 127;
+                dst[e] = r < rows ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row0 + r) : -1;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&idx_full[b]);
+            __syncwarp();
+            return true;
+        };
+        const bool solo = p.idx_bulk || !use_tbl;   // lane 0 alone runs the whole loader loop
+        if (!solo || lane == 0) {
+            if (use_tbl && (int)blockIdx.x < n_work) load_idx_tile(blockIdx.x, 0, false);
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++titer) {
+                const int w_next = w + (int)gridDim.x;
+                bool pending = use_tbl && w_next < n_work;
                 const int part = w % ksplit;
                 const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
-                for (int c = c0; c < c1; ++c) {
-                    mbar_wait(&empty[stage], ph ^ 1);
-                    mbar_arrive_expect_tx(&b_full[stage], b_bytes);
-                    const float* src = p.Wpack + (size_t)c * Cout * 64;
-                    asm volatile(
-                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                            smem_u32(tiles + (size_t)stage * stage_bytes + TC_A_TILE)),
-                        "l"(src), "r"(b_bytes), "r"(smem_u32(&b_full[stage]))
-                        : "memory");
-                    if (++stage == S) {
-                        stage = 0;
-                        ph ^= 1;
+                if (lane == 0) {
+                    for (int c = c0; c < c1; ++c) {
+                        if (pending && solo) pending = !load_idx_tile(w_next, titer + 1, true);
+                        mbar_wait(&st_free[stage], ph ^ 1);
+                        mbar_arrive_expect_tx(&st_full[stage], b_bytes);
+                        const float* src = p.Wpack + (size_t)c * Cout * 64;
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(tiles + (size_t)stage * b_bytes)),
+                            "l"(src), "r"(b_bytes), "r"(smem_u32(&st_full[stage]))
+                            : "memory");
+                        if (++stage == SB) {
+                            stage = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
+                if (!solo) __syncwarp();
+                if (pending) load_idx_tile(w_next, titer + 1, false);
             }
         }
-    } else if (warp >= 8 && warp < 12) {
-        // ===================== convert: smem -> registers -> hi/lo -> TMEM =====================
-        const int row = tid - 256;       // 0..127 = TMEM lane
-        const uint32_t lane_base = (uint32_t)((warp - 8) * 32) << 16;
-        int stage = 0;
-        uint32_t ph = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int part = w % ksplit;
-            const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
-            for (int c = c0; c < c1; ++c) {
-                mbar_wait_warp(&raw_full[stage], ph, lane);
-                TC_TS(2, c);
-                const uint8_t* st = tiles + (size_t)stage * stage_bytes;
-                float v[32], h[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 t = *reinterpret_cast<const float4*>(st + swz128(row, q));
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) h[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
-                const uint32_t taddr = tmem_base + lane_base + a_base + (uint32_t)stage * 64;
-                tmem_st32(taddr, h);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] -= h[e];
-                tmem_st32(taddr + 32, v);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[stage]);
-                TC_TS(3, c);
-                if (++stage == S) {
-                    stage = 0;
-                    ph ^= 1;
-                }
-            }
-        }
-    } else if (warp == 12) {
+    } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer =====================
         // every operand below is warp-uniform (made explicit with shfl) so the elected lane issues
         // UTCHMMA straight from uniform registers
@@ -305,51 +412,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                                ((uint32_t)(TC_ROWS >> 4) << 24);
         const uint32_t tbase = uniform(tmem_base);
         const uint32_t tiles_u32 = uniform(smem_u32(tiles));
-        const uint32_t bars_u32 = uniform(smem_u32(bars));
+        const uint32_t free_u32 = uniform(smem_u32(st_free));
         // descriptor high word is constant: SBO = 1024 B, version 1, SWIZZLE_128B
         const uint32_t desc_hi = (uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
-        int stage = 0;
-        uint32_t ph = 0;
+        int sa = 0, seqn = 0;
+        uint32_t pa = 0;
         int buf = 0;
         uint32_t acc_ph = 0;             // parity of the current use of accumulator buffer `buf`
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int part = w % ksplit;
             const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
             mbar_wait_warp(&acc_empty[buf], acc_ph ^ 1, lane);
+            // operands of the first chunk; inside the loop the wait for chunk c+1 is issued between the MMAs
+            // of chunk c so that its ~100-cycle latency overlaps the tensor pipe draining its queue (a tf32
+            // MMA of M=128, K=8 occupies the pipe for 10 + N/2 cycles: tests/micro/mma_rate.cu)
+            mbar_wait_warp(&st_full[sa], pa, lane);
             tc_fence_after();
             const uint32_t d_tmem = tbase + (uint32_t)buf * accw;
             for (int c = c0; c < c1; ++c) {
-                if (lane == 0) {
-                    mbar_wait(&b_full[stage], ph);
-                    mbar_wait(&a_full[stage], ph);
-                }
-                __syncwarp();
-                TC_TS(4, c);
-                tc_fence_after();
-                const uint32_t b_hi = tiles_u32 + (uint32_t)stage * stage_bytes + TC_A_TILE;
+                TC_TS(4, seqn);
+                const uint32_t b_hi = tiles_u32 + (uint32_t)sa * b_bytes;
                 const uint32_t b_lo = b_hi + (uint32_t)Cout * 128;
-                const uint32_t a_hi = tbase + a_base + (uint32_t)stage * 64;
-                const uint32_t empty_bar = bars_u32 + (uint32_t)stage * 8;   // empty[] is the first array
+                const uint32_t a_hi = tbase + a_base + (uint32_t)sa * 64;
+                const uint32_t free_bar = free_u32 + (uint32_t)sa * 8;
+                int sn = sa + 1;
+                uint32_t pn = pa;
+                if (sn == SA) {
+                    sn = 0;
+                    pn ^= 1;
+                }
+                const uint32_t next_bar = uniform(smem_u32(&st_full[sn]));
+                const bool more = c + 1 < c1;
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_hi + ks * 32) >> 4) & 0x3FFF);
                         const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_lo + ks * 32) >> 4) & 0x3FFF);
+                        if (ks == 3 && more) {
+                            mbar_wait_addr(next_bar, pn);
+                            tc_fence_after();
+                        }
                         tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, (c > c0 || ks > 0) ? 1u : 0u);
                         tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
                         tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_lo, idesc, 1u);
                     }
-                    // smem + TMEM stage reusable once these retire
+                    // TMEM A stage and weight stage are reusable once these retire
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     empty_bar)
+                                     free_bar)
                                  : "memory");
                 }
                 __syncwarp();
-                TC_TS(5, c);
-                if (++stage == S) {
-                    stage = 0;
-                    ph ^= 1;
-                }
+                TC_TS(5, seqn);
+                ++seqn;
+                sa = sn;
+                pa = pn;
             }
             if (elect_one()) tc_commit(&acc_full[buf]);
             __syncwarp();
@@ -364,9 +480,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
         uint32_t acc_ph = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int tile = w / ksplit;
-            mbar_wait_warp(&acc_full[buf], acc_ph, lane);
+            if (lane == 0) mbar_wait_sleep(&acc_full[buf], acc_ph, 400);  // a whole row tile away: sleep, don't spin
+            __syncwarp();
             tc_fence_after();
-            const int row = tile * TC_ROWS + warp * 32 + lane;
+            // TMEM lane -> tile row: the feeders' map (lane = 16*sub + 8*h + g holds row 4*g + 2*sub + h)
+            const int row = tile * TC_ROWS + warp * 32 + 4 * (lane & 7) + (lane >> 3);
             const bool active = row < n_out;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * accw;
             float* yr = p.Y + (size_t)row * p.ldy;
@@ -385,8 +503,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                 if (active && ksplit > 1) {
                     // partial tile of a split GEMM-K axis: fp32 reductions into the (pre-zeroed or
                     // accumulated-into) output rows
+                    // (16-byte vector reductions: a quarter of the L2 atomic operations of scalar RED.F32 - the
+                    //  atomics, not the MMAs, bounded the deep U-Net levels)
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) atomicAdd(yr + c0 + e, f[e]);
+                    for (int q = 0; q < 4; ++q)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yr + c0 + 4 * q),
+                                     "f"(f[4 * q]), "f"(f[4 * q + 1]), "f"(f[4 * q + 2]), "f"(f[4 * q + 3])
+                                     : "memory");
                 } else if (active) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -471,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
             if (v != 0.0) atomicAdd(p.stats + i, v);
         }
     }
-    if (warp == 12) {
+    if (warp == TC_WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)TC_TMEM_COLS));
     }
@@ -497,7 +620,7 @@ extern "C" long long gp_conv_tc_workspace_floats(int K, int Cin, int Cout) {
 // 1 if the tensor-core path supports this shape/alignment, else 0 (caller uses gp_conv_fwd)
 extern "C" int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy) {
     return (Cin % 4 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 256 && K >= 1 && K <= TC_MAX_TAPS &&
-           (ldx % 4 == 0) && (ldy % 4 == 0);
+           (ldx % 4 == 0) && (ldy % 4 == 0) && (long long)K * Cin + 32 < 65536;
 }
 
 extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk,
@@ -526,19 +649,23 @@ extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, 
         const char* tsp = getenv("GAPART_TC_TS");   // device pointer (decimal) of a [6*256] int64 trace buffer
         p.ts = tsp ? (long long*)strtoull(tsp, nullptr, 10) : nullptr;
     }
-    // tensor memory: [accumulator buffers | A operand stages of 64 columns (hi 32 + lo 32)]
+    // Operand ring of TC_GROUPS * spg stages: a stage = 64 TMEM columns (A hi 32 | lo 32) + one weight image in
+    // shared memory.  Two stages per feeder group decouple the feeders from the MMA round trip (feed -> MMA ->
+    // commit -> free = 2-3 k cycles); wide accumulators / weight images trade the second accumulator buffer,
+    // then the second stage, for TMEM columns / shared memory.
     p.accw = (Cout + 31) & ~31;
-    p.nbuf = (2 * p.accw + 2 * 64 <= TC_TMEM_COLS) ? 2 : 1;
-    const int s_tmem = (TC_TMEM_COLS - p.nbuf * p.accw) / 64;
-    const size_t stage_bytes = TC_A_TILE + (size_t)Cout * 256;
+    const size_t b_bytes = (size_t)Cout * 256;
     const size_t fixed = 1024 /*align*/ + (size_t)2 * K * TC_ROWS * 4 + (size_t)2 * Cout * 8 + 512;
     const size_t budget = 227 * 1024;
-    int S = (int)((budget - fixed) / stage_bytes);
-    if (S > s_tmem) S = s_tmem;
-    if (S > 8) S = 8;
-    GP_CHECK_ARG(S >= 2, "gp_conv_tc_fwd: not enough shared/tensor memory for Cout=%d", Cout);
-    p.stages = S;
-    size_t smem = fixed + (size_t)S * stage_bytes;
+    const bool smem2 = fixed + 2 * TC_GROUPS * b_bytes <= budget;
+    if (smem2 && 2 * p.accw + 2 * TC_GROUPS * 64 <= TC_TMEM_COLS) { p.nbuf = 2; p.spg = 2; }
+    else if (smem2 && p.accw + 2 * TC_GROUPS * 64 <= TC_TMEM_COLS) { p.nbuf = 1; p.spg = 2; }
+    else { p.nbuf = (2 * p.accw + TC_GROUPS * 64 <= TC_TMEM_COLS) ? 2 : 1; p.spg = 1; }
+    GP_CHECK_ARG(p.nbuf * p.accw + p.spg * TC_GROUPS * 64 <= TC_TMEM_COLS &&
+                     fixed + (size_t)p.spg * TC_GROUPS * b_bytes <= budget,
+                 "gp_conv_tc_fwd: Cout=%d exceeds tensor / shared memory", Cout);
+    p.inv_cin = (uint32_t)(0x100000000ull / (unsigned)Cin) + 1u;
+    size_t smem = fixed + (size_t)p.spg * TC_GROUPS * b_bytes;
     static thread_local bool configured = false;
     if (!configured) {
         GP_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
@@ -558,6 +685,7 @@ extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, 
         if (ksplit < 1) ksplit = 1;
     }
     p.ksplit = ksplit;
+    p.idx_bulk = (nbr != nullptr && (reinterpret_cast<size_t>(nbr) & 15) == 0 && (tbl_stride % 4) == 0) ? 1 : 0;
     int launches = 2;
     if (ksplit > 1) {
         if (!accumulate) {

@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             __syncwarp();
         } else {
             // ===================== epilogue: D[lane m][co] -> dW[co][m] (coalesced fp32 reductions) ==========
-            mbar_wait_warp(acc_full, 0, lane);
+            if (lane == 0) mbar_wait_sleep(acc_full, 0, 256);
+            __syncwarp();
             tc_fence_after();
             const int m = c_first * 32 + warp * 32 + lane;
             const bool m_ok = (warp < nch) && m < p.Ktaps * p.Cin;

@@ -1,0 +1,73 @@
+// Micro-benchmark (not a test): cycles per tcgen05.mma.kind::tf32 (M=128, K=8) vs N, A from TMEM or smem.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__global__ void __launch_bounds__(128, 1) k(int N, int a_tmem, int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t sm_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint32_t slot;
+    __shared__ uint64_t bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (256 * 128 + 128 * 128) / 4; i += 128) reinterpret_cast<float*>(sm)[i] = 0.f;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = slot;
+    if (warp == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t desc_hi = (uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+        const uint32_t b_addr = smem_u32(sm), a_addr = smem_u32(sm) + 256 * 128;
+        const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)((b_addr >> 4) & 0x3FFF);
+        const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)((a_addr >> 4) & 0x3FFF);
+        long long t0 = clock64();
+        if (elect_one()) {
+            for (int i = 0; i < iters; ++i) {
+                if (a_tmem)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                                 ::"r"(tb), "r"(tb + 256 + (i & 3) * 8), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                else
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tb), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        __syncwarp();
+        long long t1 = clock64();
+        if (lane == 0) {
+            asm volatile("{\n\t.reg .pred p;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(smem_u32(&bar)), "r"(0u) : "memory");
+            long long t2 = clock64();
+            if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512u));
+}
+int main() {
+    long long* d; cudaMalloc(&d, 16);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    const int iters = 2048;
+    for (int a_tmem : {1, 0}) for (int N : {16, 32, 48, 64, 96, 128, 256}) {
+        k<<<148, 128, 64 * 1024>>>(N, a_tmem, iters, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("A=%s N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA\n", a_tmem ? "tmem" : "smem", N, (double)h[0] / iters, (double)h[1] / iters);
+    }
+    return 0;
+}

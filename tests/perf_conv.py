@@ -20,6 +20,9 @@ ti = torch.from_numpy(idx).to(dev)
 g = ops.grid_from_coords(ti, B, shape)
 book = ops.rulebook_subm3(ti, M, g)
 print("rows", M, "pairs", int((book.nbr >= 0).sum()))
+# 16-byte aligned table rows (stride % 4 == 0) like the engine's arenas: enables the bulk-copied index tiles
+_pad = (-M) % 4
+nbr = torch.nn.functional.pad(book.nbr, (0, _pad), value=-1).contiguous() if _pad else book.nbr
 
 def timeit(fn, n=10):
     for _ in range(3): fn()
@@ -36,9 +39,9 @@ for (cin, cout, rows) in [(16, 16, M), (32, 32, M // 3), (64, 64, M // 36), (112
     dy = torch.randn(M, cout, device=dev); dw = torch.zeros_like(w)
     d_n = torch.tensor([rows], dtype=torch.int32, device=dev)
     y = torch.empty(M, cout, device=dev)
-    t_tc = timeit(lambda: ops.conv_fwd(x, w, book.nbr, 27, M, d_n_out=d_n, out=y, use_tc=True))
-    t_si = timeit(lambda: ops.conv_fwd(x, w, book.nbr, 27, M, d_n_out=d_n, out=y, use_tc=False))
-    t_wg = timeit(lambda: ops.conv_wgrad(x, dy, dw, book.nbr, 27, M, d_n))
+    t_tc = timeit(lambda: ops.conv_fwd(x, w, nbr, 27, M, d_n_out=d_n, out=y, use_tc=True))
+    t_si = timeit(lambda: ops.conv_fwd(x, w, nbr, 27, M, d_n_out=d_n, out=y, use_tc=False))
+    t_wg = timeit(lambda: ops.conv_wgrad(x, dy, dw, nbr, 27, M, d_n))
     print(f"C={cin}->{cout} rows={rows}: tc {t_tc:.1f} us  simt {t_si:.1f} us  wgrad {t_wg:.1f} us  (debug={os.environ.get('GAPART_TC_DEBUG','0')})")
 
 # timestamp trace of CTA 0 (last tile of the CTA is what remains in the buffer)
@@ -49,11 +52,12 @@ os.environ["GAPART_TC_TS"] = str(ts.data_ptr())
 x = torch.randn(M, CT, device=dev); w = torch.randn(CT, 27, CT, device=dev) * 0.1
 d_n = torch.tensor([ROWS], dtype=torch.int32, device=dev); y = torch.empty(M, CT, device=dev)
 for _ in range(3):
-    ops.conv_fwd(x, w, book.nbr, 27, M, d_n_out=d_n, out=y, use_tc=True)
+    ops.conv_fwd(x, w, nbr, 27, M, d_n_out=d_n, out=y, use_tc=True)
 torch.cuda.synchronize()
 t = ts.cpu().numpy().reshape(6, 256)
 nch = (27 * CT + 31) // 32
 t0 = t[0, 0]
-for gchunk in range(0, min(nch, 16)):
-    print(gchunk, " ".join(f"{'ggccmm'[e]}{e}={int(t[e, gchunk] - t0):6d}" for e in range(6)))
+names = ["feed", "free", "x", "fed", "mma0", "mma1"]
+for gchunk in range(40, 72):
+    print(gchunk, " ".join(f"{names[e]}={int(t[e, gchunk] - t0):6d}" for e in (0, 1, 3, 4, 5) if t[e, gchunk] != 0))
 del os.environ["GAPART_TC_TS"]

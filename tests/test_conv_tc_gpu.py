@@ -173,3 +173,29 @@ def test_tc_wgrad_tables_device_count_strided_accumulate(cuda, kind, n_rows):
         ok = idx >= 0
         ref[:, k, :] += dy[:n][ok].double().t() @ x[idx[ok]].double()
     assert rel_err(dw, ref) < 2e-5
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 32), (48, 64), (8, 16)])
+@pytest.mark.parametrize("pad", [0, 3])
+def test_tc_index_tile_paths(cuda, cin, cout, pad):
+    """16-byte aligned tables (stride % 4 == 0: index tiles arrive by cp.async.bulk, as in the engine's arenas)
+    and unaligned ones (plain-load fallback) give the same result; Cin % 16 != 0 uses zero-fill copies instead of
+    the predicated gather."""
+    t = _table(cuda, n=5000, seed=11)
+    M = t["M"]
+    stride = M + ((-M) % 4) + pad          # pad=0 -> aligned, pad=3 -> stride % 4 != 0
+    nbr = torch.full((27, stride), -1, dtype=torch.int32, device=cuda)
+    nbr[:, :M] = t["nbr"]
+    nbr[:, M:] = 123456789                 # garbage beyond the row count must never be dereferenced
+    g = torch.Generator(device="cpu").manual_seed(cin + 7 * cout + pad)
+    x = torch.randn(M, cin, generator=g).to(cuda)
+    w = (torch.randn(cout, 27, cin, generator=g) * 0.1).to(cuda)
+    y = ops.conv_fwd(x, w, nbr, 27, M, use_tc=True)
+    assert rel_err(y, _ref(x, w, t["nbr"], 27, M)) < 6e-5
+    # split-K (few row tiles) with a device-side row count
+    n = 300
+    d_n = torch.tensor([n], dtype=torch.int32, device=cuda)
+    y2 = torch.zeros(M, cout, device=cuda)
+    ops.conv_fwd(x, w, nbr, 27, M, d_n_out=d_n, out=y2, use_tc=True, rows_hint=n)
+    assert rel_err(y2[:n], _ref(x, w, t["nbr"], 27, M)[:n]) < 6e-5
+    assert float(y2[n:].abs().max()) == 0.0
