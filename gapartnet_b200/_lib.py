@@ -102,6 +102,11 @@ def check(rc: int, what: str = "") -> None:
         raise GapartError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 
 
+# int-returning queries (their value is an answer, not a status code)
+_QUERIES = ("gp_version", "gp_device_sms", "gp_conv_tc_supported", "gp_conv_wgrad_tc_supported",
+            "gp_conv_tc_ksplit", "gp_bn_cluster_ok")
+
+
 class _Caller:
     """lib.gp_xxx(...) with automatic status check."""
 
@@ -109,7 +114,7 @@ class _Caller:
         lib = load()
         fn = getattr(lib, name)
         ret = _protos[name][0]
-        if ret == "int" and name not in ("gp_version", "gp_device_sms", "gp_conv_tc_supported", "gp_conv_wgrad_tc_supported"):
+        if ret == "int" and name not in _QUERIES:
             def call(*args, _fn=fn, _name=name):
                 rc = _fn(*args)
                 if rc != 0:

@@ -617,6 +617,27 @@ extern "C" long long gp_conv_tc_workspace_floats(int K, int Cin, int Cout) {
     return (long long)tc_chunks(K, Cin) * Cout * 64;
 }
 
+// Split the GEMM-K axis when the level has too few row tiles to fill the chip (deep U-Net levels:
+// 1..30 tiles, each 50-100 chunks long).  rows_hint is the expected row count (the device-side
+// count is not known on the host); it only steers performance, never correctness.
+static int tc_ksplit(int K, int Cin, int max_out, int rows_hint) {
+    const int sms = gp_num_sms();
+    const int n_chunks = tc_chunks(K, Cin);
+    const int rows_est = (rows_hint > 0 && rows_hint < max_out) ? rows_hint : max_out;
+    const int tiles_est = gp_cdiv(rows_est, TC_ROWS);
+    int ksplit = 1;
+    if (tiles_est * 2 <= sms && n_chunks >= 4) {
+        ksplit = sms / tiles_est;
+        if (ksplit > n_chunks / 2) ksplit = n_chunks / 2;
+        if (ksplit > 32) ksplit = 32;
+        if (ksplit < 1) ksplit = 1;
+    }
+    return ksplit;
+}
+// > 1: gp_conv_tc_fwd would split the GEMM-K axis for this launch, i.e. its epilogue cannot take the BatchNorm
+// statistics (it falls back to gp_col_stats when `stats` is given)
+extern "C" int gp_conv_tc_ksplit(int K, int Cin, int max_out, int rows_hint) { return tc_ksplit(K, Cin, max_out, rows_hint); }
+
 // 1 if the tensor-core path supports this shape/alignment, else 0 (caller uses gp_conv_fwd)
 extern "C" int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy) {
     return (Cin % 4 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 256 && K >= 1 && K <= TC_MAX_TAPS &&
@@ -671,19 +692,8 @@ extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, 
         GP_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         configured = true;
     }
-    // Split the GEMM-K axis when the level has too few row tiles to fill the chip (deep U-Net levels:
-    // 1..30 tiles, each 50-100 chunks long).  rows_hint is the expected row count (the device-side
-    // count is not known here); it only steers performance, never correctness.
     const int sms = gp_num_sms();
-    const int rows_est = (rows_hint > 0 && rows_hint < max_out) ? rows_hint : max_out;
-    const int tiles_est = gp_cdiv(rows_est, TC_ROWS);
-    int ksplit = 1;
-    if (tiles_est * 2 <= sms && n_chunks >= 4) {
-        ksplit = sms / tiles_est;
-        if (ksplit > n_chunks / 2) ksplit = n_chunks / 2;
-        if (ksplit > 32) ksplit = 32;
-        if (ksplit < 1) ksplit = 1;
-    }
+    const int ksplit = tc_ksplit(K, Cin, max_out, rows_hint);
     p.ksplit = ksplit;
     p.idx_bulk = (nbr != nullptr && (reinterpret_cast<size_t>(nbr) & 15) == 0 && (tbl_stride % 4) == 0) ? 1 : 0;
     int launches = 2;

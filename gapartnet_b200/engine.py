@@ -214,19 +214,28 @@ class SparseUNetEngine:
             eng._ws_floats = max(eng._ws_floats, int(C.gp_conv_tc_workspace_floats(K, Cin, Cout)),
                                  int(C.gp_conv_tc_workspace_floats(K, Cout, Cin)))
 
+        vec_ptr = vec.data_ptr()
+
         def fwd():
             s = eng._s()
-            st = _p(stats) if eng.training else None
+            hint = eng.rows_hint[Lo]
+            train = eng.training
+            # the conv epilogue takes the BN statistics unless the GEMM-K axis is split over CTAs (deep levels);
+            # then one cluster kernel computes them itself (or gp_col_stats for a level too large for a cluster)
+            split = tc_f and C.gp_conv_tc_ksplit(K, Cin, n_out, hint) > 1
+            st = _p(stats) if (train and not split) else None
             if tc_f:
                 C.gp_conv_tc_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                                 y.ptr, y.ld, Cout, 0, st, _p(eng._ws), eng.rows_hint[Lo], s)
+                                 y.ptr, y.ld, Cout, 0, st, _p(eng._ws), hint, s)
             else:
                 C.gp_conv_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
                               y.ptr, y.ld, Cout, 0, st, s)
-            C.gp_bn_finalize(_p(stats), Cout, _p(d_n_out), n_out, g_ptr, b_ptr, eng.eps, eng.momentum,
-                             rm_ptr, rv_ptr, 0 if eng.training else 1, sc, sh, mu, istd, s)
-            C.gp_bn_apply(y.ptr, y.ld, Cout, _p(d_n_out), n_out, sc, sh, res_ptr, res_ld, int(relu),
-                          a.ptr, a.ld, s)
+            if train and split and not C.gp_bn_cluster_ok(n_out, hint):
+                C.gp_col_stats(y.ptr, y.ld, Cout, _p(d_n_out), n_out, _p(stats), s)
+                st = _p(stats)
+            C.gp_bn_fwd_fused(y.ptr, y.ld, Cout, _p(d_n_out), n_out, st, g_ptr, b_ptr, eng.eps, eng.momentum,
+                              rm_ptr, rv_ptr, 0 if train else 1, res_ptr, res_ld, int(relu), a.ptr, a.ld,
+                              vec_ptr, hint, s)
 
         self._fwd.append(fwd)
         self._n_launch_fwd += 3
@@ -255,9 +264,9 @@ class SparseUNetEngine:
 
             def bwd():
                 s = eng._s()
-                C.gp_bn_bwd(da.data_ptr(), da.stride(0), a_ptr, a.ld, y.ptr, y.ld, Cout, _p(d_n_out), n_out,
-                            mu, istd, g_ptr, _p(sums), dy.ptr, dy.ld, dres_ptr, dres_ld, dres_acc,
-                            gg_ptr, bg_ptr, 0, s)
+                C.gp_bn_bwd_fused(da.data_ptr(), da.stride(0), a_ptr, a.ld, y.ptr, y.ld, Cout, _p(d_n_out), n_out,
+                                  mu, istd, g_ptr, _p(sums), dy.ptr, dy.ld, dres_ptr, dres_ld, dres_acc,
+                                  gg_ptr, bg_ptr, 0, eng.rows_hint[Lo], s)
                 if dx_ptr is not None:
                     if tc_b and dx_ld % 4 == 0:
                         C.gp_conv_tc_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
@@ -289,13 +298,17 @@ class SparseUNetEngine:
         sc, sh, mu, istd = (vec[i].data_ptr() for i in range(4))
         eng = self
 
+        vec_ptr = vec.data_ptr()
+
         def fwd():
             s = eng._s()
-            if eng.training:
+            hint = eng.rows_hint[L]
+            st = None
+            if eng.training and not C.gp_bn_cluster_ok(n, hint):
                 C.gp_col_stats(x.ptr, x.ld, Cc, _p(d_n), n, _p(stats), s)
-            C.gp_bn_finalize(_p(stats), Cc, _p(d_n), n, g_ptr, b_ptr, eng.eps, eng.momentum, rm_ptr, rv_ptr,
-                             0 if eng.training else 1, sc, sh, mu, istd, s)
-            C.gp_bn_apply(x.ptr, x.ld, Cc, _p(d_n), n, sc, sh, None, 0, int(relu), a.ptr, a.ld, s)
+                st = _p(stats)
+            C.gp_bn_fwd_fused(x.ptr, x.ld, Cc, _p(d_n), n, st, g_ptr, b_ptr, eng.eps, eng.momentum, rm_ptr, rv_ptr,
+                              0 if eng.training else 1, None, 0, int(relu), a.ptr, a.ld, vec_ptr, hint, s)
 
         self._fwd.append(fwd)
         self._n_launch_fwd += 3
@@ -315,8 +328,9 @@ class SparseUNetEngine:
                 dst, dst_ld = scratch.data_ptr(), scratch.stride(0)
 
             def bwd():
-                C.gp_bn_bwd(da.data_ptr(), da.stride(0), a_ptr, a.ld, x.ptr, x.ld, Cc, _p(d_n), n, mu, istd,
-                            g_ptr, _p(sums), dst, dst_ld, None, 0, 0, gg_ptr, bg_ptr, 0, eng._s())
+                C.gp_bn_bwd_fused(da.data_ptr(), da.stride(0), a_ptr, a.ld, x.ptr, x.ld, Cc, _p(d_n), n, mu, istd,
+                                  g_ptr, _p(sums), dst, dst_ld, None, 0, 0, gg_ptr, bg_ptr, 0, eng.rows_hint[L],
+                                  eng._s())
 
             return bwd, 2
 

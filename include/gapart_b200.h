@@ -112,6 +112,7 @@ int gp_conv_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk
  * CTAs (partial tiles are reduced with fp32 atomics) - a performance hint only. */
 long long gp_conv_tc_workspace_floats(int K, int Cin, int Cout);
 int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy);
+int gp_conv_tc_ksplit(int K, int Cin, int max_out, int rows_hint);   /* > 1: GEMM-K split, no fused BN statistics */
 int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
                    long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K,
                    const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
@@ -148,6 +149,23 @@ int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const float* Y, 
               const int* d_n, int max_n, const float* mean, const float* invstd, const float* gamma,
               double* sums, float* dY, int lddy, float* dRes, int ldres, int res_accumulate,
               float* dgamma, float* dbeta, int zero_sums, void* stream);
+
+/* Fused forms (csrc/bn.cu): Out = [relu](BN(Y) [+ residual]) in ONE launch.
+ *   stats != NULL : per-channel sum / sumsq were accumulated by the producer (conv epilogue): finalize + apply.
+ *   stats == NULL : the statistics are computed in-kernel by one thread-block cluster (two passes over the
+ *                   level, partial sums through distributed shared memory); meant for levels that
+ *                   gp_bn_cluster_ok(max_n, rows_hint) accepts (<= 24 k expected rows), correct for any n.
+ * vec: float[4C] receives scale, shift, mean, invstd (mean / invstd feed gp_bn_bwd*). */
+int gp_bn_fwd_fused(const float* Y, int ldy, int C, const int* d_n, int max_n, const double* stats,
+                    const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                    float* running_var, int use_running, const float* residual, int ldr, int relu, float* Out,
+                    int ldo, float* vec, int rows_hint, void* stream);
+int gp_bn_cluster_ok(int max_n, int rows_hint);
+/* gp_bn_bwd with a row-count hint: small levels run as one cluster kernel (sums unused), else gp_bn_bwd. */
+int gp_bn_bwd_fused(const float* dA, int lda, const float* A, int la, const float* Y, int ldy, int C,
+                    const int* d_n, int max_n, const float* mean, const float* invstd, const float* gamma,
+                    double* sums, float* dY, int lddy, float* dRes, int ldres, int res_accumulate,
+                    float* dgamma, float* dbeta, int zero_sums, int rows_hint, void* stream);
 
 /* ---- voxel <-> point rows (pc_feature = features[pc_voxel_id], network/model.py:153,359,394) -- */
 int gp_gather_rows(const float* F, int ldf, int C, const int* idx, int N, float* Out, int ldo,

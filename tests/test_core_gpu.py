@@ -247,6 +247,61 @@ def test_bn_kernels_match_torch(cuda):
     assert rel_err(dg, bn.weight.grad) < 1e-4 and rel_err(db, bn.bias.grad) < 1e-4
 
 
+@pytest.mark.parametrize("n,Cc,given_stats", [(5000, 48, True), (5000, 48, False), (37, 112, False), (1, 16, False),
+                                               (13052, 64, False), (30000, 224, False), (3466, 80, True)])
+def test_bn_fused_kernels_match_torch(cuda, n, Cc, given_stats):
+    """gp_bn_fwd_fused (statistics from the producer, or computed by one thread-block cluster through
+    distributed shared memory) and gp_bn_bwd_fused vs torch BatchNorm1d(eps=1e-4, momentum=0.1)+ReLU+residual,
+    on strided (concat) buffers with a device-side row count."""
+    torch.manual_seed(n + Cc)
+    pad = 3
+    ybuf = (torch.randn(n + pad, 2 * Cc, device=cuda) * 3 + 1.5)
+    y = ybuf[:n, Cc:].clone().requires_grad_(True)
+    res = torch.randn(n, Cc, device=cuda).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(Cc, eps=1e-4, momentum=0.1).to(cuda)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    if n > 1:
+        ref = torch.relu(bn(y) + res)
+    else:   # torch refuses a single row in training mode; the formula still holds (var = 0)
+        ref = torch.relu((y - y.mean(0)) / torch.sqrt(y.var(0, unbiased=False) + 1e-4) * bn.weight + bn.bias + res)
+    dA = torch.randn_like(ref)
+    ref.backward(dA)
+
+    from gapartnet_b200.ops import _p, _stream
+    yv = ybuf[:, Cc:]                       # ld = 2*Cc, rows beyond n must be ignored
+    d_n = torch.tensor([n], dtype=torch.int32, device=cuda)
+    stats = None
+    if given_stats:
+        stats = torch.zeros(2 * Cc, dtype=torch.float64, device=cuda)
+        C.gp_col_stats(_p(yv), 2 * Cc, Cc, _p(d_n), n + pad, _p(stats), _stream())
+    vec = torch.empty(4, Cc, device=cuda)
+    rm, rv = torch.zeros(Cc, device=cuda), torch.ones(Cc, device=cuda)
+    out = torch.full((n + pad, Cc), -7.0, device=cuda)
+    C.gp_bn_fwd_fused(_p(yv), 2 * Cc, Cc, _p(d_n), n + pad, _p(stats), _p(bn.weight.detach()), _p(bn.bias.detach()),
+                      1e-4, 0.1, _p(rm), _p(rv), 0, _p(res.detach()), Cc, 1, _p(out), Cc, _p(vec), n, _stream())
+    assert rel_err(out[:n], ref) < (1e-5 if n > 1 else 1e-4)
+    assert float((out[n:] + 7.0).abs().max()) == 0.0
+    if n > 1:
+        assert rel_err(rm, bn.running_mean) < 1e-5 and rel_err(rv, bn.running_var) < 1e-5
+    sums = torch.zeros(2 * Cc, dtype=torch.float64, device=cuda)
+    dY, dRes = torch.empty(n, Cc, device=cuda), torch.empty(n, Cc, device=cuda)
+    dg, db = torch.zeros(Cc, device=cuda), torch.zeros(Cc, device=cuda)
+    C.gp_bn_bwd_fused(_p(dA), Cc, _p(out), Cc, _p(yv), 2 * Cc, Cc, _p(d_n), n + pad, _p(vec[2]), _p(vec[3]),
+                      _p(bn.weight.detach()), _p(sums), _p(dY), Cc, _p(dRes), Cc, 0, _p(dg), _p(db), 1, n, _stream())
+    assert rel_err(dY, y.grad) < 2e-4
+    assert rel_err(dRes, res.grad) < 1e-6
+    assert rel_err(dg, bn.weight.grad) < 2e-4 and rel_err(db, bn.bias.grad) < 2e-4
+    # eval mode: running statistics, no update
+    rm2, rv2 = rm.clone(), rv.clone()
+    C.gp_bn_fwd_fused(_p(yv), 2 * Cc, Cc, _p(d_n), n + pad, None, _p(bn.weight.detach()), _p(bn.bias.detach()),
+                      1e-4, 0.1, _p(rm2), _p(rv2), 1, None, 0, 0, _p(out), Cc, _p(vec), n, _stream())
+    ref_eval = (y.detach() - rm) / torch.sqrt(rv + 1e-4) * bn.weight.detach() + bn.bias.detach()
+    assert rel_err(out[:n], ref_eval) < 1e-5
+    assert torch.equal(rm, rm2) and torch.equal(rv, rv2)
+
+
 def test_gather_scatter_rows(cuda):
     f = torch.randn(100, 16, device=cuda)
     idx = torch.randint(-1, 100, (1000,), device=cuda, dtype=torch.int32)
