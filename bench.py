@@ -37,6 +37,9 @@ BATCH = 16
 VOXEL = 0.02
 SHAPE = 128
 METRIC = "points/sec fwd+bwd, 20k-pt scenes b16"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the L0 16->16 kernels, from the committed
+# `ncu --set full` captures (profiles/r1_summary.md); null until captured
+TRAFFIC_NCU = {"k_conv_tc": None, "k_wgrad_tc": None}
 
 
 def _peaks():
@@ -279,33 +282,53 @@ def run_ours(args):
     value = pts_per_step * args.steps / (ms_res / 1e3)
     e2e_value = pts_per_step * args.steps / (ms_e2e / 1e3)
 
-    # ---- dominant kernel: L0 SubMConv3d 16->16 launches, timed one by one with CUDA events --------
+    # ---- dominant kernels: the L0 SubMConv3d 16->16 launches (forward/dgrad operator k_conv_tc and the weight
+    # gradient k_wgrad_tc), timed one by one with CUDA events on the launching stream -------------------------
     roof = None
     if rank == 0:
-        from gapartnet_b200 import ops
-
         M0 = counts[0]
         x = torch.randn(eng.max_rows[0], 16, device=dev)
         y = torch.empty_like(x)
+        dyv = torch.randn_like(x)
         w = net.ublock.encoder_blocks[0].conv1[0].weight
-        evs = []
-        for i in range(3 + 10):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            C.gp_conv_fwd(x.data_ptr(), 16, 16, w.data_ptr(), 16, 1, 27 * 16, 0, eng.nbr[0].data_ptr(),
-                          eng.nbr[0].shape[1], 27, eng.d_n[0].data_ptr(), eng.max_rows[0], y.data_ptr(), 16, 16,
-                          0, None, torch.cuda.current_stream().cuda_stream)
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        durs = [a.elapsed_time(b) for a, b in evs[3:]]
-        dur_ms = float(np.mean(durs))
+        dw = torch.zeros_like(w)
+        ws = torch.empty(int(C.gp_conv_tc_workspace_floats(27, 16, 16)), device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        nbr, dn = eng.nbr[0], eng.d_n[0]
+        C.gp_conv_tc_fwd(x.data_ptr(), 16, 16, w.data_ptr(), 16, 1, 27 * 16, 0, nbr.data_ptr(), nbr.shape[1], 27,
+                         dn.data_ptr(), eng.max_rows[0], y.data_ptr(), 16, 16, 0, None, ws.data_ptr(), M0, st)
+
+        def time_launch(fn):
+            evs = []
+            for _ in range(3 + 10):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            return float(np.mean([a.elapsed_time(b) for a, b in evs[3:]]))
+
+        t_conv = time_launch(lambda: C.gp_conv_tc_run(
+            x.data_ptr(), 16, 16, ws.data_ptr(), nbr.data_ptr(), nbr.shape[1], 27, dn.data_ptr(), eng.max_rows[0],
+            y.data_ptr(), 16, 16, 0, None, M0, 0, st))
+        t_wgrad = time_launch(lambda: C.gp_conv_wgrad_tc(
+            x.data_ptr(), 16, 16, dyv.data_ptr(), 16, 16, nbr.data_ptr(), nbr.shape[1], 27, dn.data_ptr(),
+            eng.max_rows[0], dw.data_ptr(), 16, 1, 27 * 16, M0, st))
+        # algorithmic bytes of one launch (SURVEY 8d per-layer figure / 3 passes): X + Y (or dY) + table + W
         alg = 4.0 * (M0 * 16 + M0 * 16 + 27 * M0 + 27 * 16 * 16)
         peak, peak_src = _peaks()
-        ach = alg / (dur_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_conv_rowwise<16> (L0 SubMConv3d 16->16 fwd)", "achieved": round(ach, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
-                "launch_ms": round(dur_ms, 4), "algorithmic_bytes": alg, "peak_source": peak_src}
+
+        def entry(name, ms):
+            ach = alg / (ms / 1e3) / 1e9
+            return {"bound": "hbm", "kernel": name, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "launch_ms": round(ms, 4),
+                    "algorithmic_bytes": alg, "peak_source": peak_src}
+
+        roof = entry("k_conv_tc (L0 SubMConv3d 16->16 forward; the same kernel runs every dgrad)", t_conv)
+        roof["traffic"] = TRAFFIC_NCU.get("k_conv_tc")
+        roof["other_kernels"] = [entry("k_wgrad_tc (L0 SubMConv3d 16->16 weight gradient)", t_wgrad)]
+        roof["other_kernels"][0]["traffic"] = TRAFFIC_NCU.get("k_wgrad_tc")
         # whole-step algorithmic traffic against the step time
         per_scene = algorithmic_bytes_per_scene([c / BATCH for c in counts], 1)
         wbytes = 12.0 * sum(p.numel() for n_, p in net.named_parameters() if p.dim() == 5)

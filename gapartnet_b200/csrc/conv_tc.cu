@@ -94,6 +94,44 @@ __global__ void k_pack_weights(const float* __restrict__ W, long long w_sk, long
     *reinterpret_cast<float4*>(base + (size_t)Cout * 32 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// all weight images of a step in ONE launch (the per-conv pack launches were 140 x 3.6 us of the step)
+struct GpPackDesc {
+    const float* W; float* out; long long w_sk, w_sci, w_sco;
+    int flip_k, Ktaps, Cin, Cout, n_chunks, pad_; long long t0;    // t0: first global thread of this image
+};
+__global__ void k_pack_weights_batch(const GpPackDesc* __restrict__ descs, int n_desc, long long total) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_desc - 1;
+        while (lo < hi) {   // last descriptor with t0 <= t
+            const int mid = (lo + hi + 1) >> 1;
+            if (descs[mid].t0 <= t) lo = mid; else hi = mid - 1;
+        }
+        const GpPackDesc d = descs[lo];
+        const long long u = t - d.t0;
+        const int j = (int)(u & 7);
+        const int n = (int)((u >> 3) % d.Cout);
+        const int c = (int)(u / ((long long)d.Cout * 8));
+        float hi4[4], lo4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int kk = c * TC_KCHUNK + tc_kperm(j * 4 + e);
+            const int tap = kk / d.Cin, ci = kk - tap * d.Cin;
+            float w = 0.f;
+            if (tap < d.Ktaps) {
+                const int tw = d.flip_k ? (d.Ktaps - 1 - tap) : tap;
+                w = __ldg(d.W + tw * d.w_sk + ci * d.w_sci + n * d.w_sco);
+            }
+            const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+            hi4[e] = h;
+            lo4[e] = w - h;
+        }
+        float* base = d.out + (size_t)c * d.Cout * 64;
+        const uint32_t off = swz128(n, j) >> 2;
+        *reinterpret_cast<float4*>(base + off) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
+        *reinterpret_cast<float4*>(base + (size_t)d.Cout * 32 + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 struct TcParams {
     const float* X; int ldx; int Cin;
@@ -617,6 +655,20 @@ extern "C" long long gp_conv_tc_workspace_floats(int K, int Cin, int Cout) {
     return (long long)tc_chunks(K, Cin) * Cout * 64;
 }
 
+// descs: DEVICE array of n_desc GpPackDesc (72 bytes each, layout in include/gapart_b200.h), sorted by t0;
+// total = sum over images of n_chunks * Cout * 8 threads
+extern "C" int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long total, void* stream_) {
+    static_assert(sizeof(GpPackDesc) == 72, "GpPackDesc layout is part of the ABI");
+    if (n_desc <= 0 || total <= 0) return GP_OK;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)gp_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    k_pack_weights_batch<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const GpPackDesc*)descs, n_desc, total);
+    gp_note_launch(1);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
 // Split the GEMM-K axis when the level has too few row tiles to fill the chip (deep U-Net levels:
 // 1..30 tiles, each 50-100 chunks long).  rows_hint is the expected row count (the device-side
 // count is not known on the host); it only steers performance, never correctness.
@@ -644,10 +696,33 @@ extern "C" int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy) 
            (ldx % 4 == 0) && (ldy % 4 == 0) && (long long)K * Cin + 32 < 65536;
 }
 
-extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk,
+static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
+                          long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K, const int* d_n_out,
+                          int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats, float* wpack,
+                          int rows_hint, int prepacked, int y_zeroed, void* stream_);
+
+extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
+                              long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K,
+                              const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
+                              double* stats, float* wpack, int rows_hint, void* stream_) {
+    return conv_tc_launch(X, ldx, Cin, W, w_sk, w_sci, w_sco, flip_k, nbr, tbl_stride, K, d_n_out, max_out, Y, ldy,
+                          Cout, accumulate, stats, wpack, rows_hint, 0, 0, stream_);
+}
+
+// wpack already holds the weight image (gp_conv_tc_pack_batch); y_zeroed: the caller cleared Y, so a split-K
+// launch needs no zeroing pass of its own
+extern "C" int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride,
+                              int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
+                              double* stats, int rows_hint, int y_zeroed, void* stream_) {
+    return conv_tc_launch(X, ldx, Cin, nullptr, 0, 0, 0, 0, nbr, tbl_stride, K, d_n_out, max_out, Y, ldy, Cout,
+                          accumulate, stats, const_cast<float*>(wpack), rows_hint, 1, y_zeroed, stream_);
+}
+
+static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long long w_sk,
                               long long w_sci, long long w_sco, int flip_k, const int* nbr, int tbl_stride,
                               int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout,
-                              int accumulate, double* stats, float* wpack, int rows_hint, void* stream_) {
+                              int accumulate, double* stats, float* wpack, int rows_hint, int prepacked,
+                              int y_zeroed, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(gp_conv_tc_supported(Cin, Cout, K, ldx, ldy), "gp_conv_tc_fwd: unsupported shape Cin=%d Cout=%d K=%d",
                  Cin, Cout, K);
@@ -657,7 +732,7 @@ extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, 
     GP_CHECK_ARG(nbr != nullptr || K == 1, "gp_conv_tc_fwd: identity table needs K == 1");
     if (max_out == 0) return GP_OK;
     const int n_chunks = tc_chunks(K, Cin);
-    {
+    if (!prepacked) {
         long long total = (long long)n_chunks * Cout * 8;
         k_pack_weights<<<gp_cdiv(total, 256), 256, 0, stream>>>(W, w_sk, w_sci, w_sco, flip_k, K, Cin, Cout,
                                                                 n_chunks, wpack);
@@ -696,9 +771,9 @@ extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, 
     const int ksplit = tc_ksplit(K, Cin, max_out, rows_hint);
     p.ksplit = ksplit;
     p.idx_bulk = (nbr != nullptr && (reinterpret_cast<size_t>(nbr) & 15) == 0 && (tbl_stride % 4) == 0) ? 1 : 0;
-    int launches = 2;
+    int launches = prepacked ? 1 : 2;
     if (ksplit > 1) {
-        if (!accumulate) {
+        if (!accumulate && !y_zeroed) {
             long long total = (long long)max_out * (Cout / 4);
             long long blocks = (total + 255) / 256;
             if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;

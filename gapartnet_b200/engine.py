@@ -130,8 +130,8 @@ class SparseUNetEngine:
         # expected rows per level (performance hint for the split-K decision of the tensor-core conv);
         # mutable list read at launch time: call calibrate() after a first build_levels()
         self.rows_hint = [0] * self.depth
-        self._ws_floats = 0
-        self._ws = None
+        self._packs: List[tuple] = []
+        self._pack_descs = None
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -149,6 +149,22 @@ class SparseUNetEngine:
 
     def _s(self):
         return self._cur_stream
+
+    def _add_pack(self, w: torch.Tensor, w_sk: int, w_sci: int, w_sco: int, flip: int, K: int, cin: int,
+                  cout: int) -> torch.Tensor:
+        """register one weight image (GpPackDesc, include/gapart_b200.h) -> its device buffer"""
+        floats = int(C.gp_conv_tc_workspace_floats(K, cin, cout))
+        buf = torch.empty(floats, dtype=torch.float32, device=self.dev)
+        self._keep.append(buf)
+        n_chunks = (K * cin + 31) // 32
+        self._packs.append((w.data_ptr(), buf.data_ptr(), w_sk, w_sci, w_sco, flip, K, cin, cout, n_chunks))
+        return buf
+
+    def pack_weights(self):
+        """hi/lo-split, swizzled weight images of every tensor-core conv (forward and input-gradient
+        operators) in ONE launch; call once per optimizer step (run_forward does)."""
+        if self._pack_descs is not None:
+            C.gp_conv_tc_pack_batch(_p(self._pack_descs), self._pack_n, self._pack_total, self._bind_stream())
 
     def _bind_stream(self):
         self._cur_stream = torch.cuda.current_stream().cuda_stream
@@ -210,9 +226,9 @@ class SparseUNetEngine:
         tc_f = eng.use_tc and bool(C.gp_conv_tc_supported(Cin, Cout, K, x.ld, y.ld))
         tc_b = eng.use_tc and bool(C.gp_conv_tc_supported(Cout, Cin, K, y.ld, x.ld))
         tc_w = eng.use_tc and x.ptr % 16 == 0 and bool(C.gp_conv_wgrad_tc_supported(Cin, Cout, K, x.ld, y.ld, Cin, 1))
-        if tc_f or tc_b:
-            eng._ws_floats = max(eng._ws_floats, int(C.gp_conv_tc_workspace_floats(K, Cin, Cout)),
-                                 int(C.gp_conv_tc_workspace_floats(K, Cout, Cin)))
+        # weight images of the tensor-core convs live for the whole step: packed once by pack_weights()
+        pk_f = eng._add_pack(w, Cin, 1, K * Cin, 0, K, Cin, Cout) if tc_f else None
+        pk_b = eng._add_pack(w, Cin, K * Cin, 1, flip_b, K, Cout, Cin) if tc_b else None
 
         vec_ptr = vec.data_ptr()
 
@@ -225,8 +241,8 @@ class SparseUNetEngine:
             split = tc_f and C.gp_conv_tc_ksplit(K, Cin, n_out, hint) > 1
             st = _p(stats) if (train and not split) else None
             if tc_f:
-                C.gp_conv_tc_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                                 y.ptr, y.ld, Cout, 0, st, _p(eng._ws), hint, s)
+                C.gp_conv_tc_run(x.ptr, x.ld, Cin, pk_f.data_ptr(), _p(tbl_f), tsf, K, _p(d_n_out), n_out,
+                                 y.ptr, y.ld, Cout, 0, st, hint, 0, s)
             else:
                 C.gp_conv_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
                               y.ptr, y.ld, Cout, 0, st, s)
@@ -269,9 +285,9 @@ class SparseUNetEngine:
                                   gg_ptr, bg_ptr, 0, eng.rows_hint[Lo], s)
                 if dx_ptr is not None:
                     if tc_b and dx_ld % 4 == 0:
-                        C.gp_conv_tc_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
-                                         _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, _p(eng._ws),
-                                         eng.rows_hint[Lx], s)
+                        C.gp_conv_tc_run(dy.ptr, dy.ld, Cout, pk_b.data_ptr(), _p(tbl_b), tsb, K,
+                                         _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None,
+                                         eng.rows_hint[Lx], 0, s)
                     else:
                         C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
                                       _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
@@ -401,7 +417,19 @@ class SparseUNetEngine:
         out.grad_ready = True
         self.pc_feature = torch.empty(self.N, out.C, dtype=torch.float32, device=self.dev)
         self.d_pc_feature = torch.zeros(self.N, out.C, dtype=torch.float32, device=self.dev)
-        self._ws = torch.empty(max(self._ws_floats, 4), dtype=torch.float32, device=self.dev)
+        if self._packs:
+            import numpy as np
+            dt = np.dtype([("W", "<u8"), ("out", "<u8"), ("w_sk", "<i8"), ("w_sci", "<i8"), ("w_sco", "<i8"),
+                           ("flip", "<i4"), ("K", "<i4"), ("Cin", "<i4"), ("Cout", "<i4"), ("n_chunks", "<i4"),
+                           ("pad", "<i4"), ("t0", "<i8")])
+            assert dt.itemsize == 72
+            arr = np.zeros(len(self._packs), dtype=dt)
+            t0 = 0
+            for i, (wptr, optr, sk, sci, sco, flip, K_, cin, cout, nch) in enumerate(self._packs):
+                arr[i] = (wptr, optr, sk, sci, sco, flip, K_, cin, cout, nch, 0, t0)
+                t0 += nch * cout * 8
+            self._pack_descs = torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev)
+            self._pack_n, self._pack_total = len(self._packs), t0
         # reverse pass: instantiate backward closures in execution order
         self._bwd = []
         for mk in reversed(self._bwd_units):
@@ -441,6 +469,7 @@ class SparseUNetEngine:
 
     def run_forward(self):
         """levels must be built; -> self.pc_feature [N, C0] (static buffer)."""
+        self.pack_weights()
         s = self._bind_stream()
         if self._stat_used:
             C.gp_memset(_p(self._stat_arena), 0, self._stat_used * 8, s)

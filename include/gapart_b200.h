@@ -118,6 +118,18 @@ int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w
                    const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
                    double* stats, float* wpack, int rows_hint, void* stream);
 
+/* Weights change once per optimizer step: pack every image of the step in ONE launch, then run the convs
+ * on the stored images.  descs: DEVICE array of n_desc records of 72 bytes
+ *   { const float* W; float* out; int64 w_sk, w_sci, w_sco; int32 flip_k, K, Cin, Cout, n_chunks, pad; int64 t0 }
+ * sorted by t0 = first global thread of the image; an image takes n_chunks*Cout*8 threads (total = their sum),
+ * out = gp_conv_tc_workspace_floats(K, Cin, Cout) floats, 16-byte aligned.
+ * gp_conv_tc_run: gp_conv_tc_fwd on a packed image; y_zeroed != 0: the caller cleared Y (split-K launches then
+ * skip their own zeroing pass). */
+int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long total, void* stream);
+int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride, int K,
+                   const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats,
+                   int rows_hint, int y_zeroed, void* stream);
+
 /* dW(k', ci, co) += sum_i X[nbr[k][i], ci] * dY[i, co] */
 int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout,
                   const int* nbr, int tbl_stride, int K, const int* d_n_out, int max_out, float* dW,
