@@ -16,8 +16,8 @@
 // One CTA owns one 128-wide slice ("pass") of the (tap,ci) axis and a strided subset of the 64-row
 // tiles; partial slices are combined with fp32 red.global.  3xTF32: D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
 //
-// Warp roles (416 threads, 1 CTA/SM): 4 epilogue | 4 gather (cp.async, zero-fill, noinc barrier) |
-// 4 convert (X^T -> TMEM, dY^T -> smem) | 1 MMA issuer (elected lane, uniform operands).
+// Warp roles (416 threads, 1 CTA/SM): 4 dY^T stagers (-> smem B operand; they run the epilogue after the last
+// tile) | 4 gather (cp.async, zero-fill, noinc barrier) | 4 convert (X^T -> TMEM) | 1 MMA issuer (elected lane).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&empty[s], 1);
             mbar_init(&raw_full[s], 128);
-            mbar_init(&ab_full[s], 4);
+            mbar_init(&ab_full[s], 8);       // 4 convert warps (X^T in TMEM) + 4 stager warps (dY^T in smem)
         }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -130,46 +130,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             const int n = tid - 256;                  // TMEM lane = (tap,ci) column of this pass
             const int cc = n >> 5, col = n & 31;      // a warp = one chunk tile, lanes = its 32 columns
             const uint32_t lane_base = (uint32_t)((warp - 8) * 32) << 16;
-            const int n_b = WG_ROWS * p.Cout;         // elements of the dY tile
-            const int r_first = n / p.Cout, co_first = n - r_first * p.Cout;
-            const int step_r = 128 / p.Cout, step_co = 128 - step_r * p.Cout;
             int stage = 0;
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
-                const int row0 = (rg + t * p.row_groups) * WG_ROWS;
                 uint8_t* st = tiles + (size_t)stage * stage_bytes;
                 // raw_full fires only after the gather passed `empty` for this round, so the stage's
                 // smem B tiles and TMEM A columns are free to overwrite from here on
                 mbar_wait_warp(&raw_full[stage], ph, lane);
-                uint8_t* bh = st + WG_XBYTES;
-                {
-                    // element e = n + 128*i of the [64][Cout] dY tile; (r, co) advance without division and
-                    // 8 global loads are in flight before the first dependent store
-                    int r = r_first, co = co_first;
-                    for (int base = n; base < n_b; base += 128 * 8) {
-                        float v[8];
-                        uint32_t off[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const bool ok = base + 128 * u < n_b;
-                            const int row = row0 + r;
-                            v[u] = (ok && row < n_out) ? __ldg(p.dY + (size_t)row * p.ldy + co) : 0.f;
-                            off[u] = ok ? ((uint32_t)(r >> 5) * b_tile + swz128(co, (r & 31) >> 2) + (r & 3) * 4)
-                                        : 0xFFFFFFFFu;
-                            co += step_co;
-                            r += step_r;
-                            if (co >= p.Cout) { co -= p.Cout; ++r; }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            if (off[u] != 0xFFFFFFFFu) {
-                                const float h = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
-                                *reinterpret_cast<float*>(bh + off[u]) = h;
-                                *reinterpret_cast<float*>(bh + 2 * b_tile + off[u]) = v[u] - h;
-                            }
-                        }
-                    }
-                }
                 const uint32_t a_stage = tmem_base + lane_base + 128u + 128u * (uint32_t)stage;
                 const uint8_t* xt = st + cc * WG_XTILE + (col & 3) * 4;
                 const int pj = col >> 2;
@@ -187,7 +154,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                     tmem_st32(a_stage + 64 + half * 32, v);
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // dY^T smem writes -> tensor core
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ab_full[stage]);
@@ -231,6 +197,56 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             if (elect_one()) tc_commit(acc_full);
             __syncwarp();
         } else {
+            // ===================== dY^T stager (warps 0-3), then the epilogue =====================
+            // The [64][Cout] dY tile becomes the K-major B operand [Cout][64 rows] (hi | lo) in shared memory.  This
+            // used to sit in the convert warps: 1260 of their 2900 cycles per tile (clock64 trace), and the convert
+            // role is what bounds the kernel - the epilogue warps were idle until the last tile.
+            {
+                const int n = tid;
+                const int n_b = WG_ROWS * p.Cout;         // elements of the dY tile
+                const int r_first = n / p.Cout, co_first = n - r_first * p.Cout;
+                const int step_r = 128 / p.Cout, step_co = 128 - step_r * p.Cout;
+                int stage = 0;
+                uint32_t ph = 0;
+                for (int t = 0; t < my_tiles; ++t) {
+                    const int row0 = (rg + t * p.row_groups) * WG_ROWS;
+                    uint8_t* st = tiles + (size_t)stage * stage_bytes;
+                    mbar_wait_warp(&empty[stage], ph ^ 1, lane);     // MMAs that read this stage's B tiles retired
+                    uint8_t* bh = st + WG_XBYTES;
+                    {
+                        // element e = n + 128*i of the [64][Cout] dY tile; (r, co) advance without division and
+                        // 8 global loads are in flight before the first dependent store
+                        int r = r_first, co = co_first;
+                        for (int base = n; base < n_b; base += 128 * 8) {
+                            float v[8];
+                            uint32_t off[8];
+    #pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const bool ok = base + 128 * u < n_b;
+                                const int row = row0 + r;
+                                v[u] = (ok && row < n_out) ? __ldg(p.dY + (size_t)row * p.ldy + co) : 0.f;
+                                off[u] = ok ? ((uint32_t)(r >> 5) * b_tile + swz128(co, (r & 31) >> 2) + (r & 3) * 4)
+                                            : 0xFFFFFFFFu;
+                                co += step_co;
+                                r += step_r;
+                                if (co >= p.Cout) { co -= p.Cout; ++r; }
+                            }
+    #pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                if (off[u] != 0xFFFFFFFFu) {
+                                    const float h = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
+                                    *reinterpret_cast<float*>(bh + off[u]) = h;
+                                    *reinterpret_cast<float*>(bh + 2 * b_tile + off[u]) = v[u] - h;
+                                }
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ab_full[stage]);
+                    if (++stage == S) { stage = 0; ph ^= 1; }
+                }
+            }
             // ===================== epilogue: D[lane m][co] -> dW[co][m] (coalesced fp32 reductions) ==========
             if (lane == 0) mbar_wait_sleep(acc_full, 0, 256);
             __syncwarp();

@@ -31,9 +31,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // all issued warp instructions were these polls (ncu source page, profiles/r1_summary.md), starving the
 // producer warps that share the schedulers; ptxas drops try_wait's suspend-time hint (same SASS), so the
 // back-off is an explicit nanosleep between polls.  ns ~ how long the role can afford to oversleep.
+// Every blocking wait carries a watchdog: a protocol bug must surface as a trapped kernel with a message, never
+// as a hung GPU (legitimate waits are micro-seconds; the limit is ~1 s of polling).
+#define GP_MBAR_WATCHDOG_POLLS 40000000u
+static __device__ __noinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
+    printf("gapart_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", (int)blockIdx.x,
+           (int)threadIdx.x, addr, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
     uint32_t addr = smem_u32(bar);
-    uint32_t ok = 0;
+    uint32_t ok = 0, polls = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -42,10 +50,11 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
             : "memory");
         if (ok) break;
         __nanosleep(ns);
+        if (++polls > GP_MBAR_WATCHDOG_POLLS) mbar_timeout(addr, parity);
     }
 }
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
-    uint32_t ok = 0;
+    uint32_t ok = 0, polls = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -54,6 +63,7 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
             : "memory");
         if (ok) break;
         __nanosleep(20);
+        if (++polls > GP_MBAR_WATCHDOG_POLLS) mbar_timeout(addr, parity);
     }
 }
 #ifndef GP_MBAR_BACKOFF_NS

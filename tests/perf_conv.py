@@ -61,3 +61,18 @@ names = ["feed", "free", "x", "fed", "mma0", "mma1"]
 for gchunk in range(40, 72):
     print(gchunk, " ".join(f"{names[e]}={int(t[e, gchunk] - t0):6d}" for e in (0, 1, 3, 4, 5) if t[e, gchunk] != 0))
 del os.environ["GAPART_TC_TS"]
+
+# ---- weight-gradient kernel trace (CTA 0): gather / convert / MMA timestamps per 64-row tile
+ts = torch.zeros(8 * 256, dtype=torch.int64, device=dev)
+os.environ["GAPART_TC_TS"] = str(ts.data_ptr())
+x = torch.randn(M, 16, device=dev); dy = torch.randn(M, 16, device=dev); dw = torch.zeros(16, 27, 16, device=dev)
+d_n = torch.tensor([M], dtype=torch.int32, device=dev)
+for _ in range(3):
+    ops.conv_wgrad(x, dy, dw, nbr, 27, M, d_n)
+torch.cuda.synchronize()
+t = ts.cpu().numpy().reshape(8, 256)
+t0 = t[0, 0]
+names = ["g_free", "g_issued", "c_raw", "c_dy", "c_st", "c_fed", "m_go", "m_done"]
+for tile in range(20, 34):
+    print(tile, " ".join(f"{names[e]}={int(t[e, tile] - t0):6d}" for e in range(8)))
+del os.environ["GAPART_TC_TS"]
