@@ -99,25 +99,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             const int kk = (c_first + cc) * 32 + 4 * j;                   // GEMM-M index of this piece
             const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
             const bool col_ok = cc < nch && tap < p.Ktaps;
+            // address arithmetic hoisted out of the tile loop (the kernel is issue bound: ncu counted 7.5 k warp
+            // instructions per 64-row tile before this): one 64-bit table pointer and one 32x32->64 multiply-add per
+            // copy; destination of copy i = tile + swz128(rq + 4 i, j) = d_even/d_odd + 1024 (i >> 1)
+            const char* Xc = reinterpret_cast<const char*>(p.X) + (size_t)ci * 4;
+            const uint32_t ld_bytes = (uint32_t)p.ldx * 4u;
+            const int* tbl = p.nbr ? p.nbr + (size_t)tap * p.tbl_stride + rq : nullptr;
+            const uint32_t d_even = smem_u32(tiles) + cc * WG_XTILE + swz128(rq, j);
+            const uint32_t d_odd = smem_u32(tiles) + cc * WG_XTILE + swz128(rq + 4, j);
             int stage = 0;
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 const int row0 = (rg + t * p.row_groups) * WG_ROWS;
                 mbar_wait_warp(&empty[stage], ph ^ 1, lane);
-                uint8_t* st = tiles + (size_t)stage * stage_bytes + cc * WG_XTILE;
+                const uint32_t so = (uint32_t)stage * stage_bytes;
                 int idx[16];
+                const bool full = col_ok && row0 + WG_ROWS <= n_out;      // warp-uniform fast path
+                if (full && tbl) {
+                    const int* tp = tbl + row0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int row = row0 + rq + 4 * i;
-                    idx[i] = -1;
-                    if (col_ok && row < n_out) idx[i] = p.nbr ? __ldg(p.nbr + (size_t)tap * p.tbl_stride + row) : row;
+                    for (int i = 0; i < 16; ++i) idx[i] = __ldg(tp + 4 * i);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int row = row0 + rq + 4 * i;
+                        idx[i] = -1;
+                        if (col_ok && row < n_out) idx[i] = tbl ? __ldg(tbl + row0 + 4 * i) : row;
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float* src = p.X + (idx[i] >= 0 ? ((size_t)idx[i] * p.ldx + ci) : 0);
-                    uint32_t nbytes = idx[i] >= 0 ? 16u : 0u;
+                    const char* src = Xc + (uint64_t)(uint32_t)(idx[i] >= 0 ? idx[i] : 0) * ld_bytes;
+                    const uint32_t nbytes = idx[i] >= 0 ? 16u : 0u;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                                     smem_u32(st + swz128(rq + 4 * i, j))),
+                                     ((i & 1) ? d_odd : d_even) + so + 1024u * (i >> 1)),
                                  "l"(src), "r"(nbytes));
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[stage]))
@@ -130,6 +145,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             const int n = tid - 256;                  // TMEM lane = (tap,ci) column of this pass
             const int cc = n >> 5, col = n & 31;      // a warp = one chunk tile, lanes = its 32 columns
             const uint32_t lane_base = (uint32_t)((warp - 8) * 32) << 16;
+            uint32_t xo[8];
+#pragma unroll
+            for (int r7 = 0; r7 < 8; ++r7) xo[r7] = swz128(r7, col >> 2) + 4u * (uint32_t)(col & 3);
             int stage = 0;
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
@@ -138,14 +156,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                 // smem B tiles and TMEM A columns are free to overwrite from here on
                 mbar_wait_warp(&raw_full[stage], ph, lane);
                 const uint32_t a_stage = tmem_base + lane_base + 128u + 128u * (uint32_t)stage;
-                const uint8_t* xt = st + cc * WG_XTILE + (col & 3) * 4;
-                const int pj = col >> 2;
+                // column `col` of the chunk tile: element (row r, col) sits at swz128(r, col >> 2) + 4 (col & 3)
+                //   = 1024 (r >> 3) + xo[r & 7]: 8 per-thread offsets (hoisted), immediates for the rest
+                const uint32_t xt = smem_u32(st) + cc * WG_XTILE;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float v[32], h[32];
 #pragma unroll
                     for (int r = 0; r < 32; ++r)
-                        v[r] = cc < nch ? *reinterpret_cast<const float*>(xt + swz128(half * 32 + r, pj)) : 0.f;
+                        v[r] = cc < nch ? lds_f32(xt + xo[r & 7] + 1024u * (uint32_t)(half * 4 + (r >> 3))) : 0.f;
 #pragma unroll
                     for (int r = 0; r < 32; ++r) h[r] = __uint_as_float(__float_as_uint(v[r]) & 0xffffe000u);
                     tmem_st32(a_stage + half * 32, h);
@@ -202,44 +221,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             // used to sit in the convert warps: 1260 of their 2900 cycles per tile (clock64 trace), and the convert
             // role is what bounds the kernel - the epilogue warps were idle until the last tile.
             {
-                const int n = tid;
-                const int n_b = WG_ROWS * p.Cout;         // elements of the dY tile
-                const int r_first = n / p.Cout, co_first = n - r_first * p.Cout;
-                const int step_r = 128 / p.Cout, step_co = 128 - step_r * p.Cout;
+                // item = (output channel co, piece pc = 4 consecutive rows): 4 coalesced 4-byte loads (lanes run
+                // over co), hi/lo split, two 16-byte stores into the K-major tiles [Cout][32 rows] x 2 K-chunks
+                const int n_items = p.Cout * (WG_ROWS / 4);
                 int stage = 0;
                 uint32_t ph = 0;
                 for (int t = 0; t < my_tiles; ++t) {
                     const int row0 = (rg + t * p.row_groups) * WG_ROWS;
-                    uint8_t* st = tiles + (size_t)stage * stage_bytes;
+                    const uint32_t bh = smem_u32(tiles) + (uint32_t)stage * stage_bytes + WG_XBYTES;
                     mbar_wait_warp(&empty[stage], ph ^ 1, lane);     // MMAs that read this stage's B tiles retired
-                    uint8_t* bh = st + WG_XBYTES;
-                    {
-                        // element e = n + 128*i of the [64][Cout] dY tile; (r, co) advance without division and
-                        // 8 global loads are in flight before the first dependent store
-                        int r = r_first, co = co_first;
-                        for (int base = n; base < n_b; base += 128 * 8) {
-                            float v[8];
-                            uint32_t off[8];
-    #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const bool ok = base + 128 * u < n_b;
-                                const int row = row0 + r;
-                                v[u] = (ok && row < n_out) ? __ldg(p.dY + (size_t)row * p.ldy + co) : 0.f;
-                                off[u] = ok ? ((uint32_t)(r >> 5) * b_tile + swz128(co, (r & 31) >> 2) + (r & 3) * 4)
-                                            : 0xFFFFFFFFu;
-                                co += step_co;
-                                r += step_r;
-                                if (co >= p.Cout) { co -= p.Cout; ++r; }
-                            }
-    #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                if (off[u] != 0xFFFFFFFFu) {
-                                    const float h = __uint_as_float(__float_as_uint(v[u]) & 0xffffe000u);
-                                    *reinterpret_cast<float*>(bh + off[u]) = h;
-                                    *reinterpret_cast<float*>(bh + 2 * b_tile + off[u]) = v[u] - h;
-                                }
-                            }
-                        }
+                    int co = tid % p.Cout, pc = tid / p.Cout;
+                    const int dpc = 128 / p.Cout, dco = 128 - dpc * p.Cout;
+                    for (int it = tid; it < n_items; it += 128) {
+                        const int r = row0 + 4 * pc;
+                        const float* src = p.dY + (size_t)r * p.ldy + co;
+                        float v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[q] = (r + q < n_out) ? __ldg(src + (size_t)q * p.ldy) : 0.f;
+                        float h[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) h[q] = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
+                        const uint32_t off = bh + (uint32_t)(pc >> 3) * b_tile + swz128(co, pc & 7);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(off), "f"(h[0]), "f"(h[1]), "f"(h[2]),
+                                     "f"(h[3])
+                                     : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(off + 2 * b_tile), "f"(v[0] - h[0]),
+                                     "f"(v[1] - h[1]), "f"(v[2] - h[2]), "f"(v[3] - h[3])
+                                     : "memory");
+                        co += dco;
+                        pc += dpc;
+                        if (co >= p.Cout) { co -= p.Cout; ++pc; }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> tensor core
                     __syncwarp();
