@@ -39,7 +39,7 @@ SHAPE = 128
 METRIC = "points/sec fwd+bwd, 20k-pt scenes b16"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the L0 16->16 kernels, from the committed
 # `ncu --set full` captures (profiles/r1_summary.md); null until captured
-TRAFFIC_NCU = {"k_conv_tc": None, "k_wgrad_tc": None}
+TRAFFIC_NCU = {"k_conv_tc": 23642880.0, "k_wgrad_tc": 32341760.0}
 
 
 def _peaks():
