@@ -18,6 +18,7 @@ can consume in one call.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -121,7 +122,12 @@ class SparseUNetEngine:
         self._stats_chunks: List[torch.Tensor] = []
         self._n_launch_fwd = 0
         self._n_launch_bwd = 0
-        self._dy_pool: Dict[Tuple[int, int], _Act] = {}
+        self._dy_pool: Dict[Tuple[int, int], list] = {}
+        # weight gradients run on a side stream, overlapping the BN-backward -> dgrad chain of the next units
+        self.overlap_wgrad = os.environ.get("GAPART_OVERLAP_WGRAD", "1") != "0"
+        self._side = None
+        self._side_obj = None
+        self._main = None
         self._cur_stream = None
         self._stat_arena = None
         self._stat_used = 0
@@ -170,11 +176,17 @@ class SparseUNetEngine:
         self._cur_stream = torch.cuda.current_stream().cuda_stream
         return self._cur_stream
 
-    def _dy_scratch(self, level: int, C_: int) -> _Act:
+    def _dy_scratch(self, level: int, C_: int):
+        """-> (dY scratch, event of the weight-gradient launch that last read it or None).  Two buffers per
+        (level, C) alternate so that a unit's wgrad (side stream) may still run while the next unit of the same
+        shape already writes its dY."""
         key = (level, C_)
         if key not in self._dy_pool:
-            self._dy_pool[key] = self._new_act(level, C_)
-        return self._dy_pool[key]
+            self._dy_pool[key] = [[self._new_act(level, C_), None], [self._new_act(level, C_), None], 0]
+        pool = self._dy_pool[key]
+        slot = pool[pool[2] & 1]
+        pool[2] += 1
+        return slot
 
     def _bn_buffers(self, C_: int):
         """carve (forward stats, backward sums) from one fp64 arena that a single memset clears"""
@@ -259,8 +271,12 @@ class SparseUNetEngine:
         def make_bwd():
             # called during the reverse build pass so that first-writer flags follow execution order
             da = eng._grad_of(a)
-            # dY is consumed at once by this unit's dgrad + wgrad: one scratch per (level, C)
-            dy = eng._dy_scratch(Lo, Cout)
+            # dY is consumed by this unit's dgrad (main stream) and wgrad (side stream)
+            dy_slot = eng._dy_scratch(Lo, Cout)
+            dy, prev_reader = dy_slot[0], dy_slot[1]
+            ev_dy = torch.cuda.Event()      # dY written (main stream)
+            ev_wg = torch.cuda.Event()      # wgrad done with dY (side stream)
+            dy_slot[1] = ev_wg
             dres_ptr, dres_ld, dres_acc = None, 0, 0
             if residual is not None and residual.needs_grad:
                 rg = eng._grad_of(residual)
@@ -280,9 +296,17 @@ class SparseUNetEngine:
 
             def bwd():
                 s = eng._s()
+                ov = eng._side is not None
+                if ov and prev_reader is not None:
+                    eng._main.wait_event(prev_reader)     # the previous user's wgrad still reads this dY buffer
                 C.gp_bn_bwd_fused(da.data_ptr(), da.stride(0), a_ptr, a.ld, y.ptr, y.ld, Cout, _p(d_n_out), n_out,
                                   mu, istd, g_ptr, _p(sums), dy.ptr, dy.ld, dres_ptr, dres_ld, dres_acc,
                                   gg_ptr, bg_ptr, 0, eng.rows_hint[Lo], s)
+                sw = s
+                if ov:
+                    ev_dy.record(eng._main)
+                    eng._side.wait_event(ev_dy)
+                    sw = eng._side.cuda_stream
                 if dx_ptr is not None:
                     if tc_b and dx_ld % 4 == 0:
                         C.gp_conv_tc_run(dy.ptr, dy.ld, Cout, pk_b.data_ptr(), _p(tbl_b), tsb, K,
@@ -293,10 +317,12 @@ class SparseUNetEngine:
                                       _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
                 if tc_w:
                     C.gp_conv_wgrad_tc(x.ptr, x.ld, Cin, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                                       wg_ptr, Cin, 1, K * Cin, eng.rows_hint[Lo], s)
+                                       wg_ptr, Cin, 1, K * Cin, eng.rows_hint[Lo], sw)
                 else:
                     C.gp_conv_wgrad(x.ptr, x.ld, Cin, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                                    wg_ptr, Cin, 1, K * Cin, 0, s)
+                                    wg_ptr, Cin, 1, K * Cin, 0, sw)
+                if ov:
+                    ev_wg.record(eng._side)
 
             return bwd, n_launch
 
@@ -483,12 +509,22 @@ class SparseUNetEngine:
     def run_backward(self):
         """consumes self.d_pc_feature [N, C0]; accumulates into every parameter's .grad."""
         s = self._bind_stream()
+        if self.overlap_wgrad:
+            if self._side_obj is None:
+                self._side_obj = torch.cuda.Stream(device=self.dev)
+            self._main = torch.cuda.current_stream()
+            self._side = self._side_obj
+        else:
+            self._side = None
         og = self.out_grad
         C.gp_memset(_p(og), 0, og.numel() * 4, s)
         C.gp_scatter_add_rows(_p(self.d_pc_feature), self.d_pc_feature.stride(0), og.shape[1],
                               _p(self.pc_voxel_id), self.N, _p(og), og.stride(0), s)
         for op in self._bwd:
             op()
+        if self._side is not None:
+            self._main.wait_stream(self._side)     # join: every weight gradient is complete on return
+            self._side = None
 
     # convenience --------------------------------------------------------------------------------
     def load_points(self, points: torch.Tensor, batch_offsets: torch.Tensor):
