@@ -283,11 +283,37 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(
     }
 }
 
+// rows per block of the reduction kernels: enough blocks with work to fill the chip (>= 4 per SM) for the
+// EXPECTED row count - the static bound max_n can be 100x larger at the deeper levels
+static int reduce_rows_per_block(int rows_est) {
+    int rpb = gp_cdiv(rows_est, gp_num_sms() * 4);
+    rpb = (rpb + 15) & ~15;
+    if (rpb < 32) rpb = 32;
+    if (rpb > 512) rpb = 512;
+    return rpb;
+}
+
+static int bn_bwd_launch(const float* dA, int lda, const float* A, int la, const float* Y, int ldy,
+                         int C, const int* d_n, int max_n, const float* mean, const float* invstd,
+                         const float* gamma, double* sums, float* dY, int lddy, float* dRes, int ldres,
+                         int res_accumulate, float* dgamma, float* dbeta, int zero_sums, int rows_hint,
+                         void* stream_);
+
 extern "C" int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const float* Y, int ldy,
                          int C, const int* d_n, int max_n, const float* mean, const float* invstd,
                          const float* gamma, double* sums, float* dY, int lddy, float* dRes, int ldres,
                          int res_accumulate, float* dgamma, float* dbeta, int zero_sums, void* stream_) {
+    return bn_bwd_launch(dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, sums, dY, lddy, dRes, ldres,
+                         res_accumulate, dgamma, dbeta, zero_sums, 0, stream_);
+}
+
+static int bn_bwd_launch(const float* dA, int lda, const float* A, int la, const float* Y, int ldy,
+                         int C, const int* d_n, int max_n, const float* mean, const float* invstd,
+                         const float* gamma, double* sums, float* dY, int lddy, float* dRes, int ldres,
+                         int res_accumulate, float* dgamma, float* dbeta, int zero_sums, int rows_hint,
+                         void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    const int rows_est = (rows_hint > 0 && rows_hint < max_n) ? rows_hint : max_n;
     GP_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024, "gp_bn_bwd: C must be a multiple of 4");
     GP_CHECK_ARG(lda % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && (!A || la % 4 == 0) &&
                      (!dRes || ldres % 4 == 0),
@@ -297,10 +323,10 @@ extern "C" int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const
                  "gp_bn_bwd: pointers must be 16-byte aligned");
     if (max_n == 0) return GP_OK;
     if (zero_sums) GP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), stream));
-    int rows_per_block = 512;
+    const int rows_per_block = reduce_rows_per_block(rows_est);
     k_bn_bwd_reduce<<<gp_cdiv(max_n, rows_per_block), 256, (size_t)(256 / (C / 4)) * 2 * C * sizeof(float), stream>>>(
         dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, sums, rows_per_block);
-    k_bn_bwd_apply<<<ew_grid((long long)max_n * (C / 4)), 256, 0, stream>>>(
+    k_bn_bwd_apply<<<ew_grid((long long)rows_est * (C / 4)), 256, 0, stream>>>(
         dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, sums, dY, lddy, dRes, ldres,
         res_accumulate, dgamma, dbeta);
     gp_note_launch(2);
@@ -316,7 +342,7 @@ extern "C" int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const
 //     from the 2C sums (cheap) inside the apply kernel -> no finalize launch;
 //   * statistics unknown (split-K conv) or backward: ONE thread-block cluster (8 or 16 CTAs)
 //     makes both passes over the level - partial sums are exchanged through distributed shared
-//     memory, the cluster barrier replaces the kernel boundary.  A level of <= ~24 k rows is
+//     memory, the cluster barrier replaces the kernel boundary.  A level of a few thousand rows is
 //     L2 resident, so the second pass re-reads from L2.
 // ---------------------------------------------------------------------------------------------
 #include <cooperative_groups.h>
@@ -462,8 +488,10 @@ __global__ void __launch_bounds__(BNF_THREADS) k_bn_fwd_cluster(const BnFwdArgs 
     cluster.sync();   // nobody leaves while its partial sums may still be read
 }
 
-static int bn_cluster_size(int rows_est) { return rows_est <= 6000 ? 8 : 16; }
-#define BN_CLUSTER_MAX_ROWS 24000
+// one cluster = at most 16 SMs: measured 30 us for the backward of a 13 k-row level vs ~20 us for the two-kernel
+// path, so only levels up to 6 k expected rows take the cluster kernels
+static int bn_cluster_size(int rows_est) { return rows_est <= 1500 ? 8 : 16; }
+#define BN_CLUSTER_MAX_ROWS 6000
 
 template <typename Args>
 static int launch_cluster(void (*kern)(const Args), const Args& a, int cl, cudaStream_t stream) {
@@ -549,10 +577,10 @@ __global__ void __launch_bounds__(BNF_THREADS) k_bn_bwd_cluster(const BnBwdArgs 
     }
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     if (rl < rpb) {
-        for (int rb = r0 + rl; rb < r1; rb += 2 * rpb) {
-            float4 g[2], av[2], y[2];
+        for (int rb = r0 + rl; rb < r1; rb += 4 * rpb) {
+            float4 g[4], av[4], y[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 const int r = rb + u * rpb;
                 const bool ok = r < r1;
                 g[u] = ok ? ldg4(a.dA + (size_t)r * a.lda + cgi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -560,7 +588,7 @@ __global__ void __launch_bounds__(BNF_THREADS) k_bn_bwd_cluster(const BnBwdArgs 
                 y[u] = ok ? ldg4(a.Y + (size_t)r * a.ldy + cgi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 if (!(av[u].x > 0.f)) g[u].x = 0.f;
                 if (!(av[u].y > 0.f)) g[u].y = 0.f;
                 if (!(av[u].z > 0.f)) g[u].z = 0.f;
@@ -629,7 +657,7 @@ __global__ void __launch_bounds__(BNF_THREADS) k_bn_bwd_cluster(const BnBwdArgs 
     cluster.sync();
 }
 
-/* gp_bn_bwd with a launch hint: levels of <= 24 k expected rows run as ONE cluster kernel (no sums scratch, no
+/* gp_bn_bwd with a launch hint: levels of <= 6 k expected rows run as ONE cluster kernel (no sums scratch, no
  * memset); larger ones as the two-kernel path above with grids sized from the hint. */
 extern "C" int gp_bn_bwd_fused(const float* dA, int lda, const float* A, int la, const float* Y, int ldy, int C,
                                const int* d_n, int max_n, const float* mean, const float* invstd,
@@ -639,8 +667,8 @@ extern "C" int gp_bn_bwd_fused(const float* dA, int lda, const float* A, int la,
     cudaStream_t stream = (cudaStream_t)stream_;
     const int rows_est = (rows_hint > 0 && rows_hint < max_n) ? rows_hint : max_n;
     if (rows_est > BN_CLUSTER_MAX_ROWS || C > BNF_MAXC)
-        return gp_bn_bwd(dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, sums, dY, lddy, dRes, ldres,
-                         res_accumulate, dgamma, dbeta, zero_sums, stream_);
+        return bn_bwd_launch(dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, sums, dY, lddy, dRes, ldres,
+                             res_accumulate, dgamma, dbeta, zero_sums, rows_hint, stream_);
     GP_CHECK_ARG(C > 0 && C % 4 == 0, "gp_bn_bwd_fused: C must be a multiple of 4");
     GP_CHECK_ARG(lda % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && (!A || la % 4 == 0) && (!dRes || ldres % 4 == 0),
                  "gp_bn_bwd_fused: strides must be multiples of 4");

@@ -166,7 +166,7 @@ int gp_bn_bwd(const float* dA, int lda, const float* A, int la, const float* Y, 
  *   stats != NULL : per-channel sum / sumsq were accumulated by the producer (conv epilogue): finalize + apply.
  *   stats == NULL : the statistics are computed in-kernel by one thread-block cluster (two passes over the
  *                   level, partial sums through distributed shared memory); meant for levels that
- *                   gp_bn_cluster_ok(max_n, rows_hint) accepts (<= 24 k expected rows), correct for any n.
+ *                   gp_bn_cluster_ok(max_n, rows_hint) accepts (<= 6 k expected rows), correct for any n.
  * vec: float[4C] receives scale, shift, mean, invstd (mean / invstd feed gp_bn_bwd*). */
 int gp_bn_fwd_fused(const float* Y, int ldy, int C, const int* d_n, int max_n, const double* stats,
                     const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
