@@ -97,7 +97,8 @@ __global__ void k_pack_weights(const float* __restrict__ W, long long w_sk, long
 // all weight images of a step in ONE launch (the per-conv pack launches were 140 x 3.6 us of the step)
 struct GpPackDesc {
     const float* W; float* out; long long w_sk, w_sci, w_sco;
-    int flip_k, Ktaps, Cin, Cout, n_chunks, pad_; long long t0;    // t0: first global thread of this image
+    int flip_k, Ktaps, Cin, Cout, n_chunks, cin_real; long long t0;   // t0: first global thread of this image;
+                                                                      // cin_real (0 = Cin): channels ci >= cin_real are zero padding
 };
 __global__ void k_pack_weights_batch(const GpPackDesc* __restrict__ descs, int n_desc, long long total) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -117,7 +118,7 @@ __global__ void k_pack_weights_batch(const GpPackDesc* __restrict__ descs, int n
             const int kk = c * TC_KCHUNK + tc_kperm(j * 4 + e);
             const int tap = kk / d.Cin, ci = kk - tap * d.Cin;
             float w = 0.f;
-            if (tap < d.Ktaps) {
+            if (tap < d.Ktaps && (d.cin_real == 0 || ci < d.cin_real)) {
                 const int tw = d.flip_k ? (d.Ktaps - 1 - tap) : tap;
                 w = __ldg(d.W + tw * d.w_sk + ci * d.w_sci + n * d.w_sco);
             }

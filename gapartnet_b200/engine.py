@@ -157,13 +157,13 @@ class SparseUNetEngine:
         return self._cur_stream
 
     def _add_pack(self, w: torch.Tensor, w_sk: int, w_sci: int, w_sco: int, flip: int, K: int, cin: int,
-                  cout: int) -> torch.Tensor:
+                  cout: int, cin_real: int = 0) -> torch.Tensor:
         """register one weight image (GpPackDesc, include/gapart_b200.h) -> its device buffer"""
         floats = int(C.gp_conv_tc_workspace_floats(K, cin, cout))
         buf = torch.empty(floats, dtype=torch.float32, device=self.dev)
         self._keep.append(buf)
         n_chunks = (K * cin + 31) // 32
-        self._packs.append((w.data_ptr(), buf.data_ptr(), w_sk, w_sci, w_sco, flip, K, cin, cout, n_chunks))
+        self._packs.append((w.data_ptr(), buf.data_ptr(), w_sk, w_sci, w_sco, flip, K, cin, cout, n_chunks, cin_real))
         return buf
 
     def pack_weights(self):
@@ -235,6 +235,17 @@ class SparseUNetEngine:
         res_ptr, res_ld = (residual.ptr, residual.ld) if residual is not None else (None, 0)
         eng = self
 
+        # Cin not a multiple of 4 (the stem's 6 input channels): run the tensor-core kernels on a zero-padded copy
+        # of the input; the weight image is padded by the packer, the weight gradient is cut back afterwards
+        Cin_p = (Cin + 3) & ~3
+        pad_in = (eng.use_tc and Cin_p != Cin and not x.needs_grad and
+                  bool(C.gp_conv_tc_supported(Cin_p, Cout, K, Cin_p, y.ld)) and
+                  bool(C.gp_conv_wgrad_tc_supported(Cin_p, Cout, K, Cin_p, y.ld, Cin_p, 1)))
+        if pad_in:
+            xpad = torch.zeros(self.max_rows[Lx], Cin_p, dtype=torch.float32, device=self.dev)
+            dw_pad = torch.zeros(Cout, K, Cin_p, dtype=torch.float32, device=self.dev)
+            self._keep += [xpad, dw_pad]
+            pk_pad = eng._add_pack(w, Cin, 1, K * Cin, 0, K, Cin_p, Cout, cin_real=Cin)
         tc_f = eng.use_tc and bool(C.gp_conv_tc_supported(Cin, Cout, K, x.ld, y.ld))
         tc_b = eng.use_tc and bool(C.gp_conv_tc_supported(Cout, Cin, K, y.ld, x.ld))
         tc_w = eng.use_tc and x.ptr % 16 == 0 and bool(C.gp_conv_wgrad_tc_supported(Cin, Cout, K, x.ld, y.ld, Cin, 1))
@@ -250,9 +261,13 @@ class SparseUNetEngine:
             train = eng.training
             # the conv epilogue takes the BN statistics unless the GEMM-K axis is split over CTAs (deep levels);
             # then one cluster kernel computes them itself (or gp_col_stats for a level too large for a cluster)
-            split = tc_f and C.gp_conv_tc_ksplit(K, Cin, n_out, hint) > 1
+            split = (tc_f or pad_in) and C.gp_conv_tc_ksplit(K, Cin_p if pad_in else Cin, n_out, hint) > 1
             st = _p(stats) if (train and not split) else None
-            if tc_f:
+            if pad_in:
+                xpad[:, :Cin].copy_(x.t)     # rows beyond the device count are never read
+                C.gp_conv_tc_run(xpad.data_ptr(), Cin_p, Cin_p, pk_pad.data_ptr(), _p(tbl_f), tsf, K, _p(d_n_out),
+                                 n_out, y.ptr, y.ld, Cout, 0, st, hint, 0, s)
+            elif tc_f:
                 C.gp_conv_tc_run(x.ptr, x.ld, Cin, pk_f.data_ptr(), _p(tbl_f), tsf, K, _p(d_n_out), n_out,
                                  y.ptr, y.ld, Cout, 0, st, hint, 0, s)
             else:
@@ -315,7 +330,14 @@ class SparseUNetEngine:
                     else:
                         C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
                                       _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
-                if tc_w:
+                if pad_in:
+                    with torch.cuda.stream(eng._side if ov else torch.cuda.current_stream()):
+                        dw_pad.zero_()
+                        C.gp_conv_wgrad_tc(xpad.data_ptr(), Cin_p, Cin_p, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K,
+                                           _p(d_n_out), n_out, dw_pad.data_ptr(), Cin_p, 1, K * Cin_p,
+                                           eng.rows_hint[Lo], sw)
+                        wg.view(Cout, K, Cin).add_(dw_pad[:, :, :Cin])
+                elif tc_w:
                     C.gp_conv_wgrad_tc(x.ptr, x.ld, Cin, dy.ptr, dy.ld, Cout, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
                                        wg_ptr, Cin, 1, K * Cin, eng.rows_hint[Lo], sw)
                 else:
@@ -451,8 +473,8 @@ class SparseUNetEngine:
             assert dt.itemsize == 72
             arr = np.zeros(len(self._packs), dtype=dt)
             t0 = 0
-            for i, (wptr, optr, sk, sci, sco, flip, K_, cin, cout, nch) in enumerate(self._packs):
-                arr[i] = (wptr, optr, sk, sci, sco, flip, K_, cin, cout, nch, 0, t0)
+            for i, (wptr, optr, sk, sci, sco, flip, K_, cin, cout, nch, creal) in enumerate(self._packs):
+                arr[i] = (wptr, optr, sk, sci, sco, flip, K_, cin, cout, nch, creal, t0)
                 t0 += nch * cout * 8
             self._pack_descs = torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev)
             self._pack_n, self._pack_total = len(self._packs), t0

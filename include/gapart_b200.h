@@ -120,7 +120,8 @@ int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w
 
 /* Weights change once per optimizer step: pack every image of the step in ONE launch, then run the convs
  * on the stored images.  descs: DEVICE array of n_desc records of 72 bytes
- *   { const float* W; float* out; int64 w_sk, w_sci, w_sco; int32 flip_k, K, Cin, Cout, n_chunks, pad; int64 t0 }
+ *   { const float* W; float* out; int64 w_sk, w_sci, w_sco; int32 flip_k, K, Cin, Cout, n_chunks, cin_real; int64 t0 }
+ * (cin_real != 0: W has only cin_real input channels, the image is zero-padded to Cin - the stem's 6 -> 8)
  * sorted by t0 = first global thread of the image; an image takes n_chunks*Cout*8 threads (total = their sum),
  * out = gp_conv_tc_workspace_floats(K, Cin, Cout) floats, 16-byte aligned.
  * gp_conv_tc_run: gp_conv_tc_fwd on a packed image; y_zeroed != 0: the caller cleared Y (split-K launches then
