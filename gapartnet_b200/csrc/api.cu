@@ -32,6 +32,16 @@ int gp_num_sms() {
 
 extern "C" int gp_device_sms(void) { return gp_num_sms(); }
 
+#include <stdlib.h>
+bool gp_pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("GAPART_PDL");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached == 1;
+}
+
 #include <atomic>
 static std::atomic<long long> g_launches{0};
 void gp_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

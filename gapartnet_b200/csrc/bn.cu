@@ -61,6 +61,8 @@ extern "C" int gp_bn_finalize(const double* stats, int C, const int* d_n, int ma
 __global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ Y, int ldy, int C,
                                                    const int* __restrict__ d_n, int max_n,
                                                    double* __restrict__ stats, int rows_per_block) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     int n = gp_rows(d_n, max_n);
     int r0 = blockIdx.x * rows_per_block;
     if (r0 >= n) return;
@@ -108,8 +110,9 @@ extern "C" int gp_col_stats(const float* Y, int ldy, int C, const int* d_n, int 
     GP_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 1024 && ldy % 4 == 0, "gp_col_stats: C must be a multiple of 4");
     if (max_n == 0) return GP_OK;
     int rows_per_block = 512;
-    k_col_stats<<<gp_cdiv(max_n, rows_per_block), 256, (size_t)(256 / (C / 4)) * 2 * C * sizeof(float), stream>>>(
-        Y, ldy, C, d_n, max_n, stats, rows_per_block);
+    GP_CUDA(gp_launch(k_col_stats, dim3(gp_cdiv(max_n, rows_per_block)), dim3(256),
+                      (size_t)(256 / (C / 4)) * 2 * C * sizeof(float), stream, Y, ldy, C, d_n, max_n, stats,
+                      rows_per_block));
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
@@ -178,6 +181,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
                                                        const float* __restrict__ mean,
                                                        const float* __restrict__ invstd,
                                                        double* __restrict__ sums, int rows_per_block) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     int n = gp_rows(d_n, max_n);
     int r0 = blockIdx.x * rows_per_block;
     if (r0 >= n) return;
@@ -236,6 +241,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const double* __restrict__ sums, float* __restrict__ dY, int lddy, float* __restrict__ dRes,
     int ldres, int res_accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     int n = gp_rows(d_n, max_n);
     if (blockIdx.x == 0 && dgamma) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -324,11 +331,12 @@ static int bn_bwd_launch(const float* dA, int lda, const float* A, int la, const
     if (max_n == 0) return GP_OK;
     if (zero_sums) GP_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), stream));
     const int rows_per_block = reduce_rows_per_block(rows_est);
-    k_bn_bwd_reduce<<<gp_cdiv(max_n, rows_per_block), 256, (size_t)(256 / (C / 4)) * 2 * C * sizeof(float), stream>>>(
-        dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, sums, rows_per_block);
-    k_bn_bwd_apply<<<ew_grid((long long)rows_est * (C / 4)), 256, 0, stream>>>(
-        dA, lda, A, la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, sums, dY, lddy, dRes, ldres,
-        res_accumulate, dgamma, dbeta);
+    GP_CUDA(gp_launch(k_bn_bwd_reduce, dim3(gp_cdiv(max_n, rows_per_block)), dim3(256),
+                      (size_t)(256 / (C / 4)) * 2 * C * sizeof(float), stream, dA, lda, A, la, Y, ldy, C, d_n, max_n,
+                      mean, invstd, sums, rows_per_block));
+    GP_CUDA(gp_launch(k_bn_bwd_apply, dim3(ew_grid((long long)rows_est * (C / 4))), dim3(256), 0, stream, dA, lda, A,
+                      la, Y, ldy, C, d_n, max_n, mean, invstd, gamma, (const double*)sums, dY, lddy, dRes, ldres,
+                      res_accumulate, dgamma, dbeta));
     gp_note_launch(2);
     GP_LAUNCH_CHECK();
     return GP_OK;
@@ -424,6 +432,8 @@ __device__ __forceinline__ void bnf_apply_rows(const BnFwdArgs& a, int r0, int r
 
 // statistics given: finalize (per block, redundant) + apply
 __global__ void __launch_bounds__(BNF_THREADS) k_bn_fwd_stats(const BnFwdArgs a) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     __shared__ __align__(16) float s_scale[BNF_MAXC], s_shift[BNF_MAXC];
     const int n = gp_rows(a.d_n, a.max_n);
     bnf_finalize(a, n, a.stats, a.stats ? a.stats + a.C : nullptr, s_scale, s_shift, blockIdx.x == 0);
@@ -435,6 +445,8 @@ __global__ void __launch_bounds__(BNF_THREADS) k_bn_fwd_stats(const BnFwdArgs a)
 
 // statistics computed here: one cluster, two passes
 __global__ void __launch_bounds__(BNF_THREADS) k_bn_fwd_cluster(const BnFwdArgs a) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ __align__(16) float s_scale[BNF_MAXC], s_shift[BNF_MAXC];
     __shared__ float part[BNF_THREADS * 8];          // [rpb][2C] fp32 partials (rpb * cpr <= 512)
@@ -503,13 +515,15 @@ static int launch_cluster(void (*kern)(const Args), const Args& a, int cl, cudaS
     cfg.blockDim = dim3(BNF_THREADS, 1, 1);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = gp_pdl_enabled() ? 2 : 1;
     GP_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     return GP_OK;
 }
@@ -535,8 +549,7 @@ extern "C" int gp_bn_fwd_fused(const float* Y, int ldy, int C, const int* d_n, i
         const int cap = gp_num_sms() * 4;
         if (grid > cap) grid = cap;
         if (grid < 1) grid = 1;
-        k_bn_fwd_stats<<<grid, BNF_THREADS, 0, stream>>>(a);
-        GP_LAUNCH_CHECK();
+        GP_CUDA(gp_launch(k_bn_fwd_stats, dim3(grid), dim3(BNF_THREADS), 0, stream, a));
     } else {
         int rc = launch_cluster(k_bn_fwd_cluster, a, bn_cluster_size(rows_est), stream);
         if (rc != GP_OK) return rc;
@@ -559,6 +572,8 @@ struct BnBwdArgs {
 
 // backward in one cluster: pass 1 sums of dz and dz*xhat (dz = dA * (A > 0)), DSMEM exchange, pass 2 dY / dRes
 __global__ void __launch_bounds__(BNF_THREADS) k_bn_bwd_cluster(const BnBwdArgs a) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float part[BNF_THREADS * 8];
     __shared__ double my_part[2 * BNF_MAXC];
@@ -690,6 +705,8 @@ extern "C" int gp_bn_bwd_fused(const float* dA, int lda, const float* A, int la,
 __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ F, int ldf, int C,
                                                      const int* __restrict__ idx, int N,
                                                      float* __restrict__ Out, int ldo) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     int cpr = C >> 2;
     long long total = (long long)N * cpr;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -706,6 +723,8 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ F
 __global__ void __launch_bounds__(256) k_scatter_add_rows(const float* __restrict__ dOut, int ldo,
                                                           int C, const int* __restrict__ idx, int N,
                                                           float* __restrict__ dF, int ldf) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     long long total = (long long)N * C;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -721,7 +740,8 @@ extern "C" int gp_gather_rows(const float* F, int ldf, int C, const int* idx, in
     GP_CHECK_ARG(C > 0 && C % 4 == 0 && ldf % 4 == 0 && ldo % 4 == 0, "gp_gather_rows: C %% 4 != 0");
     GP_CHECK_ARG(GP_ALIGNED16(F) && GP_ALIGNED16(Out), "gp_gather_rows: pointers must be 16-byte aligned");
     if (N == 0) return GP_OK;
-    k_gather_rows<<<ew_grid((long long)N * (C / 4)), 256, 0, stream>>>(F, ldf, C, idx, N, Out, ldo);
+    GP_CUDA(gp_launch(k_gather_rows, dim3(ew_grid((long long)N * (C / 4))), dim3(256), 0, stream, F, ldf, C, idx, N, Out,
+                      ldo));
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
@@ -732,7 +752,8 @@ extern "C" int gp_scatter_add_rows(const float* dOut, int ldo, int C, const int*
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(C > 0, "gp_scatter_add_rows: C <= 0");
     if (N == 0) return GP_OK;
-    k_scatter_add_rows<<<ew_grid((long long)N * C), 256, 0, stream>>>(dOut, ldo, C, idx, N, dF, ldf);
+    GP_CUDA(gp_launch(k_scatter_add_rows, dim3(ew_grid((long long)N * C)), dim3(256), 0, stream, dOut, ldo, C, idx, N, dF,
+                      ldf));
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;

@@ -86,3 +86,31 @@ __device__ __forceinline__ int warp_scan_incl(int v, int lane) {
     }
     return v;
 }
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// The step is a chain of ~500 short dependent kernels; at the deep U-Net levels a kernel runs 8-15 us and the
+// launch gap between dependent graph nodes is a visible fraction of that.  Kernels launched through gp_launch()
+// carry cudaLaunchAttributeProgrammaticStreamSerialization: the next grid may be scheduled while the current one
+// drains (its CTAs take an SM as soon as one frees up) and runs its prologue; gp_pdl_wait() - executed by every such
+// kernel before it touches global memory - blocks until the predecessor grid has completed and flushed, so the
+// data dependencies (RAW and WAR) are those of ordinary stream order.  GAPART_PDL=0 launches without the attribute
+// (the two instructions are then no-ops).
+__device__ __forceinline__ void gp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gp_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool gp_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gp_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gp_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}

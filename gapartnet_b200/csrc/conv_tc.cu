@@ -101,6 +101,8 @@ struct GpPackDesc {
                                                                       // cin_real (0 = Cin): channels ci >= cin_real are zero padding
 };
 __global__ void k_pack_weights_batch(const GpPackDesc* __restrict__ descs, int n_desc, long long total) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = n_desc - 1;
         while (lo < hi) {   // last descriptor with t0 <= t
@@ -176,12 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(idx_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_out = gp_rows(p.d_n_out, p.max_out);
-    const int n_tiles = (n_out + TC_ROWS - 1) / TC_ROWS;
-    // work item w = tile * ksplit + part: chunks [part*n/ksplit, (part+1)*n/ksplit) of row tile `tile`.
-    // ksplit > 1 spreads the few row tiles of the deep U-Net levels (1..30 tiles) over the whole chip.
     const int ksplit = p.ksplit;
-    const int n_work = n_tiles * ksplit;
     const int nbuf = p.nbuf;
     const uint32_t accw = (uint32_t)p.accw;
     const uint32_t a_base = (uint32_t)nbuf * accw;            // first TMEM column of the A stages
@@ -211,6 +208,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, tensor-memory allocation) overlapped the tail of the previous kernel; global
+    // memory is touched only from here on
+    gp_pdl_wait();
+    gp_pdl_trigger();
+    const int n_out = gp_rows(p.d_n_out, p.max_out);
+    const int n_tiles = (n_out + TC_ROWS - 1) / TC_ROWS;
+    // work item w = tile * ksplit + part: chunks [part*n/ksplit, (part+1)*n/ksplit) of row tile `tile`.
+    // ksplit > 1 spreads the few row tiles of the deep U-Net levels (1..30 tiles) over the whole chip.
+    const int n_work = n_tiles * ksplit;
 
     if (warp >= 4 && warp < TC_WARP_MMA) {
         // ===================== feeders: global -> registers -> hi/lo -> TMEM =====================
@@ -641,6 +647,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
 
 // zero the first n (device count) rows of a strided [rows, C] matrix
 __global__ void k_zero_rows(float* __restrict__ Y, int ldy, int C, const int* __restrict__ d_n, int max_n) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
     const int n = gp_rows(d_n, max_n), cpr = C >> 2;
     const long long total = (long long)n * cpr;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -664,7 +672,8 @@ extern "C" int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long to
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)gp_num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    k_pack_weights_batch<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const GpPackDesc*)descs, n_desc, total);
+    GP_CUDA(gp_launch(k_pack_weights_batch, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream_,
+                      (const GpPackDesc*)descs, n_desc, total));
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
@@ -778,14 +787,14 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
             long long total = (long long)max_out * (Cout / 4);
             long long blocks = (total + 255) / 256;
             if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-            k_zero_rows<<<(int)blocks, 256, 0, stream>>>(Y, ldy, Cout, d_n_out, max_out);
+            GP_CUDA(gp_launch(k_zero_rows, dim3((int)blocks), dim3(256), 0, stream, Y, ldy, Cout, d_n_out, max_out));
             ++launches;
         }
         p.stats = nullptr;   // partial tiles: the BatchNorm statistics are taken by gp_col_stats below
     }
     long long work = (long long)gp_cdiv(max_out, TC_ROWS) * ksplit;
     int grid = work < sms ? (int)work : sms;
-    k_conv_tc<<<grid, TC_THREADS, smem, stream>>>(p);
+    GP_CUDA(gp_launch(k_conv_tc, dim3(grid), dim3(TC_THREADS), smem, stream, p));
     gp_note_launch(launches);
     GP_LAUNCH_CHECK();
     if (ksplit > 1 && stats) return gp_col_stats(Y, ldy, Cout, d_n_out, max_out, stats, stream_);

@@ -64,12 +64,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_out = gp_rows(p.d_n_out, p.max_out);
-    const int n_rt = (n_out + WG_ROWS - 1) / WG_ROWS;
     const int pass = blockIdx.x % p.passes, rg = blockIdx.x / p.passes;
     const int c_first = pass * WG_NCH;
     const int nch = min(WG_NCH, p.n_chunks - c_first);          // chunks of this pass (>= 1)
-    const int my_tiles = rg < n_rt ? (n_rt - 1 - rg) / p.row_groups + 1 : 0;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -89,6 +86,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    gp_pdl_wait();          // prologue above overlapped the previous kernel's tail (common.cuh)
+    gp_pdl_trigger();
+    const int n_out = gp_rows(p.d_n_out, p.max_out);
+    const int n_rt = (n_out + WG_ROWS - 1) / WG_ROWS;
+    const int my_tiles = rg < n_rt ? (n_rt - 1 - rg) / p.row_groups + 1 : 0;
     // TMEM columns: D [0,128) (Cout <= 128 used) | A stage s at 128 + 128*s: hi [0,64) lo [64,128)
 
     if (my_tiles > 0) {
@@ -329,7 +331,7 @@ extern "C" int gp_conv_wgrad_tc(const float* X, int ldx, int Cin, const float* d
         GP_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         configured = true;
     }
-    k_wgrad_tc<<<p.passes * rgs, WG_THREADS, smem, stream>>>(p);
+    GP_CUDA(gp_launch(k_wgrad_tc, dim3(p.passes * rgs), dim3(WG_THREADS), smem, stream, p));
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
