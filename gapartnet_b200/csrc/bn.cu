@@ -253,40 +253,52 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(
     float inv_n = n > 0 ? 1.f / (float)n : 0.f;
     int cpr = C >> 2;
     long long total = (long long)n * cpr;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        int r = (int)(t / cpr), cg = (int)(t - (long long)r * cpr);
-        float4 g = ldg4(dA + (size_t)r * lda + cg * 4);
-        if (A) {
-            float4 a = ldg4(A + (size_t)r * la + cg * 4);
-            if (!(a.x > 0.f)) g.x = 0.f;
-            if (!(a.y > 0.f)) g.y = 0.f;
-            if (!(a.z > 0.f)) g.z = 0.f;
-            if (!(a.w > 0.f)) g.w = 0.f;
-        }
-        if (dRes) {
-            float4* p = reinterpret_cast<float4*>(dRes + (size_t)r * ldres + cg * 4);
-            float4 o = g;
-            if (res_accumulate) {
-                float4 e = *p;
-                o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
-            }
-            *p = o;
-        }
-        float4 y = ldg4(Y + (size_t)r * ldy + cg * 4);
-        float4 mu = ldg4(mean + cg * 4), is = ldg4(invstd + cg * 4), ga = ldg4(gamma + cg * 4);
-        float sb[4], sg[4];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // two row pieces per iteration: 6-8 independent 16-byte loads in flight per thread
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += 2 * stride) {
+        float4 g[2], av[2], y[2], e[2];
+        int rr[2], cgs[2];
+        bool ok[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            sb[j] = (float)sums[cg * 4 + j] * inv_n;
-            sg[j] = (float)sums[C + cg * 4 + j] * inv_n;
+        for (int u = 0; u < 2; ++u) {
+            const long long t = t0 + u * stride;
+            ok[u] = t < total;
+            const long long tt = ok[u] ? t : t0;
+            rr[u] = (int)(tt / cpr);
+            cgs[u] = (int)(tt - (long long)rr[u] * cpr);
+            g[u] = ldg4(dA + (size_t)rr[u] * lda + cgs[u] * 4);
+            av[u] = A ? ldg4(A + (size_t)rr[u] * la + cgs[u] * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            y[u] = ldg4(Y + (size_t)rr[u] * ldy + cgs[u] * 4);
+            e[u] = (dRes && res_accumulate) ? *reinterpret_cast<const float4*>(dRes + (size_t)rr[u] * ldres + cgs[u] * 4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float4 o;
-        o.x = ga.x * is.x * (g.x - sb[0] - (y.x - mu.x) * is.x * sg[0]);
-        o.y = ga.y * is.y * (g.y - sb[1] - (y.y - mu.y) * is.y * sg[1]);
-        o.z = ga.z * is.z * (g.z - sb[2] - (y.z - mu.z) * is.z * sg[2]);
-        o.w = ga.w * is.w * (g.w - sb[3] - (y.w - mu.w) * is.w * sg[3]);
-        *reinterpret_cast<float4*>(dY + (size_t)r * lddy + cg * 4) = o;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) break;
+            const int r = rr[u], cg = cgs[u];
+            if (!(av[u].x > 0.f)) g[u].x = 0.f;
+            if (!(av[u].y > 0.f)) g[u].y = 0.f;
+            if (!(av[u].z > 0.f)) g[u].z = 0.f;
+            if (!(av[u].w > 0.f)) g[u].w = 0.f;
+            if (dRes) {
+                float4 o = g[u];
+                o.x += e[u].x; o.y += e[u].y; o.z += e[u].z; o.w += e[u].w;
+                *reinterpret_cast<float4*>(dRes + (size_t)r * ldres + cg * 4) = o;
+            }
+            float4 mu = ldg4(mean + cg * 4), is = ldg4(invstd + cg * 4), ga = ldg4(gamma + cg * 4);
+            float sb[4], sg[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sb[j] = (float)sums[cg * 4 + j] * inv_n;
+                sg[j] = (float)sums[C + cg * 4 + j] * inv_n;
+            }
+            float4 o;
+            o.x = ga.x * is.x * (g[u].x - sb[0] - (y[u].x - mu.x) * is.x * sg[0]);
+            o.y = ga.y * is.y * (g[u].y - sb[1] - (y[u].y - mu.y) * is.y * sg[1]);
+            o.z = ga.z * is.z * (g[u].z - sb[2] - (y[u].z - mu.z) * is.z * sg[2]);
+            o.w = ga.w * is.w * (g[u].w - sb[3] - (y[u].w - mu.w) * is.w * sg[3]);
+            *reinterpret_cast<float4*>(dY + (size_t)r * lddy + cg * 4) = o;
+        }
     }
 }
 
@@ -415,18 +427,28 @@ __device__ __forceinline__ void bnf_apply_rows(const BnFwdArgs& a, int r0, int r
                                                const float* s_scale, const float* s_shift) {
     const float4 sc = *reinterpret_cast<const float4*>(s_scale + cgi * 4);
     const float4 sh = *reinterpret_cast<const float4*>(s_shift + cgi * 4);
-    for (int r = r0 + rl; r < r1; r += row_step) {
-        float4 v = ldg4(a.Y + (size_t)r * a.ldy + cgi * 4);
-        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-        if (a.res) {
-            const float4 rr = ldg4(a.res + (size_t)r * a.ldr + cgi * 4);
-            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+    // 4 rows per iteration: up to 8 independent 16-byte loads in flight per thread (the loop is latency bound)
+    for (int rb = r0 + rl; rb < r1; rb += 4 * row_step) {
+        float4 v[4], rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = rb + u * row_step;
+            const bool ok = r < r1;
+            v[u] = ok ? ldg4(a.Y + (size_t)r * a.ldy + cgi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[u] = (ok && a.res) ? ldg4(a.res + (size_t)r * a.ldr + cgi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (a.relu) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = rb + u * row_step;
+            if (r >= r1) break;
+            float4 o;
+            o.x = fmaf(v[u].x, sc.x, sh.x) + rr[u].x; o.y = fmaf(v[u].y, sc.y, sh.y) + rr[u].y;
+            o.z = fmaf(v[u].z, sc.z, sh.z) + rr[u].z; o.w = fmaf(v[u].w, sc.w, sh.w) + rr[u].w;
+            if (a.relu) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(a.Out + (size_t)r * a.ldo + cgi * 4) = o;
         }
-        *reinterpret_cast<float4*>(a.Out + (size_t)r * a.ldo + cgi * 4) = v;
     }
 }
 
