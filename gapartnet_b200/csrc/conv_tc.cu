@@ -147,6 +147,8 @@ struct TcParams {
     int ksplit;      // >1: the GEMM-K (chunk) axis of a row tile is split over CTAs, partial tiles are added atomically
     int idx_bulk;    // 1: a tile's neighbour indices arrive as Ktaps cp.async.bulk copies (16-byte aligned table)
     uint32_t inv_cin;  // floor(2^32 / Cin) + 1: kk / Cin == umulhi(kk, inv_cin) for kk < 2^16
+    int* zero_sync;  // != NULL: split-K launch zeroes its own output rows (epilogue warps, before the first reduction)
+                     // and synchronises the grid through these two counters {zeroed CTAs, finished CTAs}
     long long* ts;   // optional timestamp trace [6][256] of CTA 0 (perf experiments)
 };
 
@@ -521,6 +523,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
         }
     } else {
         // ===================== epilogue (warps 0-3) =====================
+        if (p.zero_sync) {
+            // split-K partial tiles are added with red.global: the output rows must be zero first.  These warps idle
+            // until the first accumulator is ready, so they clear the rows here (one launch less per conv) and the
+            // grid meets on a counter before anybody reduces into them.
+            const int cpr = Cout >> 2;
+            const long long total = (long long)n_out * cpr;
+            for (long long t = (long long)blockIdx.x * 128 + tid; t < total; t += (long long)gridDim.x * 128) {
+                const int r = (int)(t / cpr), cg = (int)(t - (long long)r * cpr);
+                *reinterpret_cast<float4*>(p.Y + (size_t)r * p.ldy + cg * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __threadfence();
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (tid == 0) atomicAdd(p.zero_sync, 1);
+        }
+        bool zero_seen = p.zero_sync == nullptr;
         int buf = 0;
         uint32_t acc_ph = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -528,6 +545,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
             if (lane == 0) mbar_wait_sleep(&acc_full[buf], acc_ph, 400);  // a whole row tile away: sleep, don't spin
             __syncwarp();
             tc_fence_after();
+            if (!zero_seen) {
+                if (lane == 0) {
+                    int seen, polls = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.zero_sync) : "memory");
+                        if (seen < (int)gridDim.x) {
+                            __nanosleep(64);
+                            if (++polls > 20000000) mbar_timeout(0xdead0000u, (uint32_t)seen);
+                        }
+                    } while (seen < (int)gridDim.x);
+                }
+                __syncwarp();
+                zero_seen = true;
+            }
             // TMEM lane -> tile row: the feeders' map (lane = 16*sub + 8*h + g holds row 4*g + 2*sub + h)
             const int row = tile * TC_ROWS + warp * 32 + 4 * (lane & 7) + (lane >> 3);
             const bool active = row < n_out;
@@ -639,6 +670,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
             if (v != 0.0) atomicAdd(p.stats + i, v);
         }
     }
+    if (p.zero_sync && tid == 0) {
+        // the last CTA to finish re-arms the two counters for the next launch (nobody polls them any more)
+        __threadfence();
+        if (atomicAdd(p.zero_sync + 1, 1) == (int)gridDim.x - 1) {
+            p.zero_sync[0] = 0;
+            p.zero_sync[1] = 0;
+            __threadfence();
+        }
+    }
     if (warp == TC_WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)TC_TMEM_COLS));
@@ -709,30 +749,30 @@ extern "C" int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy) 
 static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
                           long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K, const int* d_n_out,
                           int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats, float* wpack,
-                          int rows_hint, int prepacked, int y_zeroed, void* stream_);
+                          int rows_hint, int prepacked, int* zero_sync, void* stream_);
 
 extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
                               long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K,
                               const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
                               double* stats, float* wpack, int rows_hint, void* stream_) {
     return conv_tc_launch(X, ldx, Cin, W, w_sk, w_sci, w_sco, flip_k, nbr, tbl_stride, K, d_n_out, max_out, Y, ldy,
-                          Cout, accumulate, stats, wpack, rows_hint, 0, 0, stream_);
+                          Cout, accumulate, stats, wpack, rows_hint, 0, nullptr, stream_);
 }
 
-// wpack already holds the weight image (gp_conv_tc_pack_batch); y_zeroed: the caller cleared Y, so a split-K
-// launch needs no zeroing pass of its own
+// wpack already holds the weight image (gp_conv_tc_pack_batch); zero_sync (optional): two zero-initialised ints the
+// caller keeps for this stream - a split-K launch then clears its output rows itself instead of a k_zero_rows pass
 extern "C" int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride,
                               int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
-                              double* stats, int rows_hint, int y_zeroed, void* stream_) {
+                              double* stats, int rows_hint, int* zero_sync, void* stream_) {
     return conv_tc_launch(X, ldx, Cin, nullptr, 0, 0, 0, 0, nbr, tbl_stride, K, d_n_out, max_out, Y, ldy, Cout,
-                          accumulate, stats, const_cast<float*>(wpack), rows_hint, 1, y_zeroed, stream_);
+                          accumulate, stats, const_cast<float*>(wpack), rows_hint, 1, zero_sync, stream_);
 }
 
 static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long long w_sk,
                               long long w_sci, long long w_sco, int flip_k, const int* nbr, int tbl_stride,
                               int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout,
                               int accumulate, double* stats, float* wpack, int rows_hint, int prepacked,
-                              int y_zeroed, void* stream_) {
+                              int* zero_sync, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(gp_conv_tc_supported(Cin, Cout, K, ldx, ldy), "gp_conv_tc_fwd: unsupported shape Cin=%d Cout=%d K=%d",
                  Cin, Cout, K);
@@ -782,8 +822,11 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
     p.ksplit = ksplit;
     p.idx_bulk = (nbr != nullptr && (reinterpret_cast<size_t>(nbr) & 15) == 0 && (tbl_stride % 4) == 0) ? 1 : 0;
     int launches = prepacked ? 1 : 2;
+    p.zero_sync = nullptr;
     if (ksplit > 1) {
-        if (!accumulate && !y_zeroed) {
+        if (!accumulate && zero_sync) {
+            p.zero_sync = zero_sync;
+        } else if (!accumulate) {
             long long total = (long long)max_out * (Cout / 4);
             long long blocks = (total + 255) / 256;
             if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;

@@ -137,6 +137,8 @@ class SparseUNetEngine:
         # mutable list read at launch time: call calibrate() after a first build_levels()
         self.rows_hint = [0] * self.depth
         self._packs: List[tuple] = []
+        # grid counters of the split-K convs' in-kernel output zeroing (main stream only; re-armed by each launch)
+        self._zero_sync = torch.zeros(2, dtype=torch.int32, device=dev)
         self._pack_descs = None
         self._build()
 
@@ -266,10 +268,10 @@ class SparseUNetEngine:
             if pad_in:
                 xpad[:, :Cin].copy_(x.t)     # rows beyond the device count are never read
                 C.gp_conv_tc_run(xpad.data_ptr(), Cin_p, Cin_p, pk_pad.data_ptr(), _p(tbl_f), tsf, K, _p(d_n_out),
-                                 n_out, y.ptr, y.ld, Cout, 0, st, hint, 0, s)
+                                 n_out, y.ptr, y.ld, Cout, 0, st, hint, _p(eng._zero_sync), s)
             elif tc_f:
                 C.gp_conv_tc_run(x.ptr, x.ld, Cin, pk_f.data_ptr(), _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                                 y.ptr, y.ld, Cout, 0, st, hint, 0, s)
+                                 y.ptr, y.ld, Cout, 0, st, hint, _p(eng._zero_sync), s)
             else:
                 C.gp_conv_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
                               y.ptr, y.ld, Cout, 0, st, s)
@@ -326,7 +328,7 @@ class SparseUNetEngine:
                     if tc_b and dx_ld % 4 == 0:
                         C.gp_conv_tc_run(dy.ptr, dy.ld, Cout, pk_b.data_ptr(), _p(tbl_b), tsb, K,
                                          _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None,
-                                         eng.rows_hint[Lx], 0, s)
+                                         eng.rows_hint[Lx], _p(eng._zero_sync), s)
                     else:
                         C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
                                       _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)

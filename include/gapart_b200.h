@@ -124,12 +124,13 @@ int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w
  * (cin_real != 0: W has only cin_real input channels, the image is zero-padded to Cin - the stem's 6 -> 8)
  * sorted by t0 = first global thread of the image; an image takes n_chunks*Cout*8 threads (total = their sum),
  * out = gp_conv_tc_workspace_floats(K, Cin, Cout) floats, 16-byte aligned.
- * gp_conv_tc_run: gp_conv_tc_fwd on a packed image; y_zeroed != 0: the caller cleared Y (split-K launches then
- * skip their own zeroing pass). */
+ * gp_conv_tc_run: gp_conv_tc_fwd on a packed image; zero_sync (optional): two zero-initialised ints owned by the
+ * caller for this stream - split-K launches then clear their output rows in-kernel (grid counter) instead of a
+ * separate zeroing launch; the kernel re-arms the counters before it exits. */
 int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long total, void* stream);
 int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride, int K,
                    const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats,
-                   int rows_hint, int y_zeroed, void* stream);
+                   int rows_hint, int* zero_sync, void* stream);
 
 /* dW(k', ci, co) += sum_i X[nbr[k][i], ci] * dY[i, co] */
 int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout,
