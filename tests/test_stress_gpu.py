@@ -74,3 +74,43 @@ def test_dense_scene_stress_properties(cuda):
         # the second forward would advance BatchNorm's running statistics again - irrelevant for the gradients
     denom = float(grads[0].abs().max())
     assert float((grads[0] - grads[1]).abs().max()) / denom < 1e-4
+
+
+def test_full_size_tensor_core_path_within_tolerance(cuda):
+    """BASELINE.json configs[2] at FULL size (16 scenes x 20 000 points, voxel 0.02, the bench workload): the tcgen05
+    3xTF32 path against the exact-fp32 FFMA path of the same engine on identical weights and inputs.  north_star
+    tolerance: per-point logits within 1e-3 relative (here: of the largest logit; measured 1.2e-5).  Gradients are
+    compared at 5e-3 of the largest gradient: measured 1.0e-3, all of it at the two deepest levels (58 / 233 rows) whose
+    BatchNorm backward over a handful of rows amplifies fp32 noise ~1000x - two runs of the SAME tensor-core path already
+    differ by 5.6e-5 there because of the order of the fp32 atomics (tests/debug_grad_tol.py prints the per-layer
+    breakdown); the small-scale engine tests pin the gradients against the fp64 oracle."""
+    import copy
+
+    import gapartnet_b200.spconv.pytorch as sp
+
+    B, n, voxel, S = 16, 20000, 0.02, 128
+    scs = [synthetic.planes(3000 + b, n) for b in range(B)]
+    torch.manual_seed(23333)
+    net_tc = mirror.build_sparse_unet(sp, 6, [16, 32, 48, 64, 80, 96, 112], 2).to(cuda)
+    net_ff = copy.deepcopy(net_tc)
+    pts = torch.from_numpy(np.concatenate([s.points for s in scs])).to(cuda)
+    off = torch.arange(B + 1, dtype=torch.int64, device=cuda) * n
+    head = torch.randn(10, 16, device=cuda) * 0.1
+    outs = []
+    for net, tc in ((net_tc, True), (net_ff, False)):
+        eng = SparseUNetEngine(net, batch=B, max_points=B * n, spatial_shape=(S, S, S), voxel_size=voxel,
+                               in_channels=6, use_tc=tc)
+        eng.load_points(pts, off)
+        eng.build_levels()
+        eng.calibrate()
+        eng.zero_grad()
+        f = eng.run_forward()
+        logits = f @ head.t()
+        eng.d_pc_feature.copy_((torch.softmax(logits, 1) - 0.1) @ head / (B * n))
+        eng.run_backward()
+        torch.cuda.synchronize()
+        outs.append((logits.clone(), eng.flat_grad.clone()))
+        del eng
+    (l_tc, g_tc), (l_ff, g_ff) = outs
+    assert float((l_tc - l_ff).abs().max()) / float(l_ff.abs().max()) < 1e-3
+    assert float((g_tc - g_ff).abs().max()) / float(g_ff.abs().max()) < 5e-3
