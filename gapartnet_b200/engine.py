@@ -128,6 +128,8 @@ class SparseUNetEngine:
         self._side = None
         self._side_obj = None
         self._main = None
+        self._lvl_events = None
+        self._pack_event = None
         self._cur_stream = None
         self._stat_arena = None
         self._stat_used = 0
@@ -427,6 +429,7 @@ class SparseUNetEngine:
         if not has_child:
             return x
         skip = x
+        self._fwd.append(lambda L1=L + 1: self._wait_level(L1))
         d = self._unit_conv_bn(skip, ub.downsample[0], ub.downsample[1], L + 1, "down", relu=True)
         d = self._ublock(ub.ublock, d)
         up = self._unit_conv_bn(d, ub.upsample[0], ub.upsample[1], L, "up", relu=True, into=cat[:, :c0])
@@ -488,10 +491,27 @@ class SparseUNetEngine:
             self._n_launch_bwd += nl
 
     # ------------------------------------------------------------------------------------------
-    def build_levels(self):
-        """voxelize (points -> level 0) + every rulebook of the step; no host sync."""
+    def build_levels(self, overlap: bool = False):
+        """voxelize (points -> level 0) + every rulebook of the step; no host sync.
+
+        overlap=True: only level 0 is built on the calling stream; the strided rulebooks and the pair tables of the
+        deeper levels run on a side stream while the level-0 convolutions of run_forward() already execute, and
+        run_forward() waits for a level's event right before its first use.  Only for build_levels() immediately
+        followed by run_forward() on the same stream (the side stream is joined there - also inside a captured
+        graph); level_counts() / calibrate() join as well."""
         s = self._bind_stream()
         N, B = self.N, self.B
+        if overlap:
+            if self._side_obj is None:
+                self._side_obj = torch.cuda.Stream(device=self.dev)
+            main, side = torch.cuda.current_stream(), self._side_obj
+            ev0 = torch.cuda.Event()
+            ev0.record(main)
+            side.wait_event(ev0)
+            if self._pack_descs is not None:      # the step's weight images, off the critical path
+                C.gp_conv_tc_pack_batch(_p(self._pack_descs), self._pack_n, self._pack_total, side.cuda_stream)
+                self._pack_event = torch.cuda.Event()
+                self._pack_event.record(side)
         C.gp_scene_range(_p(self.points), self.points.stride(0), _p(self.batch_offsets), B, 1e-4,
                          _p(self.rmin), _p(self.rmax), s)
         g0 = self.grids[0]
@@ -500,31 +520,68 @@ class SparseUNetEngine:
                       _p(self.rmax), 1, *g0.shape, _p(g0.words), _p(g0.prefix), _p(self.scan_tmp[0]),
                       _p(self.pt_cell), self.max_rows[0], _p(self.vox_feats), _p(self.vox_cnt),
                       _p(self.coords[0]), _p(self.pc_voxel_id), _p(self.d_n[0]), _p(self.batch_splits), s)
-        self._rulebooks(s)
+        if not overlap:
+            self._lvl_events = None
+            self._rulebooks(s, range(self.depth))
+            return
+        ev_vox = torch.cuda.Event()
+        ev_vox.record(main)
+        side.wait_event(ev_vox)
+        self._lvl_events = [None] * self.depth
+        self._subm_table(0, s)
+        ss = side.cuda_stream
+        for L in range(self.depth - 1):
+            self._down_table(L, ss)
+            self._subm_table(L + 1, ss)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            self._lvl_events[L + 1] = ev
 
-    def _rulebooks(self, s):
-        B = self.B
-        for L in range(self.depth):
-            g = self.grids[L]
-            C.gp_rulebook_subm3(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], B, *g.shape,
-                                _p(g.words), _p(g.prefix), _p(g.row_of_rank), _p(self.nbr[L]),
-                                self.nbr[L].shape[1], s)
+    def _wait_level(self, L: int):
+        """forward plan hook: level L's tables (built on the side stream by build_levels(overlap=True)) are ready"""
+        if self._lvl_events is not None and self._lvl_events[L] is not None:
+            torch.cuda.current_stream().wait_event(self._lvl_events[L])
+            self._lvl_events[L] = None
+
+    def _join_levels(self):
+        if self._lvl_events is not None:
+            for L in range(self.depth):
+                self._wait_level(L)
+            self._lvl_events = None
+
+    def _subm_table(self, L: int, s):
+        g = self.grids[L]
+        C.gp_rulebook_subm3(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], self.B, *g.shape,
+                            _p(g.words), _p(g.prefix), _p(g.row_of_rank), _p(self.nbr[L]),
+                            self.nbr[L].shape[1], s)
+
+    def _down_table(self, L: int, s):
+        g, g2 = self.grids[L], self.grids[L + 1]
+        C.gp_rulebook_down2(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], self.B, *g.shape,
+                            _p(g2.words), _p(g2.prefix), _p(self.scan_tmp[L + 1]),
+                            self.max_rows[L + 1], _p(self.coords[L + 1]), _p(self.d_n[L + 1]),
+                            _p(self.child[L]), self.child[L].shape[1], _p(self.parent8[L]),
+                            self.parent8[L].shape[1], s)
+
+    def _rulebooks(self, s, levels):
+        for L in levels:
+            self._subm_table(L, s)
             if L + 1 < self.depth:
-                g2 = self.grids[L + 1]
-                C.gp_rulebook_down2(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], B, *g.shape,
-                                    _p(g2.words), _p(g2.prefix), _p(self.scan_tmp[L + 1]),
-                                    self.max_rows[L + 1], _p(self.coords[L + 1]), _p(self.d_n[L + 1]),
-                                    _p(self.child[L]), self.child[L].shape[1], _p(self.parent8[L]),
-                                    self.parent8[L].shape[1], s)
+                self._down_table(L, s)
 
     def run_forward(self):
         """levels must be built; -> self.pc_feature [N, C0] (static buffer)."""
-        self.pack_weights()
+        if self._pack_event is not None:      # packed on the side stream by build_levels(overlap=True)
+            torch.cuda.current_stream().wait_event(self._pack_event)
+            self._pack_event = None
+        else:
+            self.pack_weights()
         s = self._bind_stream()
         if self._stat_used:
             C.gp_memset(_p(self._stat_arena), 0, self._stat_used * 8, s)
         for op in self._fwd:
             op()
+        self._join_levels()
         o = self.out_act
         C.gp_gather_rows(o.ptr, o.ld, o.C, _p(self.pc_voxel_id), self.N, _p(self.pc_feature),
                          self.pc_feature.stride(0), s)
@@ -573,6 +630,7 @@ class SparseUNetEngine:
 
     def level_counts(self) -> List[int]:
         """host copy of the per-level row counts (syncs; diagnostics only)."""
+        self._join_levels()
         return [int(d.item()) for d in self.d_n]
 
     @property
