@@ -36,7 +36,9 @@ struct WgParams {
     const int* nbr; int tbl_stride; int Ktaps;
     const int* d_n_out; int max_out;
     float* dW; long long w_sco;       // KRSC: dW[co * w_sco + tap * Cin + ci]
-    int n_chunks; int passes; int row_groups; int stages;
+    int n_chunks; int passes; int row_groups;
+    int raw_stages;   // R: gathered-X tiles in shared memory (gather -> convert)
+    int op_stages;    // T: operand ring = TMEM A stage + dY^T smem tiles (convert/stager -> MMA), T <= 3 (tensor memory)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -51,16 +53,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int S = p.stages;
+    const int R = p.raw_stages, T = p.op_stages;
     const uint32_t b_tile = (uint32_t)p.Cout * 128;             // one K-chunk (32 rows) of dY^T: [Cout][32 floats]
     const uint32_t b_bytes = 4 * b_tile;                        // hi: 2 K-chunks, lo: 2 K-chunks
-    const uint32_t stage_bytes = WG_XBYTES + b_bytes;
-    uint8_t* tiles = smem;                                      // [S][X raw 32 KB | dY^T hi | dY^T lo]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)S * stage_bytes);
-    uint64_t* empty = bars;                    // [S] MMA finished with the stage (smem B + TMEM A)
-    uint64_t* raw_full = bars + S;             // [S] gathered X rows landed
-    uint64_t* ab_full = bars + 2 * S;          // [S] X^T hi/lo in TMEM and dY^T hi/lo in smem ready
-    uint64_t* acc_full = bars + 3 * S;         // [1]
+    // Two rings: the gathered tiles need depth (a cp.async tile lands ~3 k cycles after it is issued), the operand
+    // ring is capped at 3 stages by tensor memory (D 128 columns + 3 x 128 A columns).  With one shared ring the
+    // gather could only start once the MMAs of tile t-3 had retired and the whole kernel ran as a latency chain.
+    uint8_t* tiles = smem;                                      // [R][X raw 32 KB]
+    uint8_t* btiles = tiles + (size_t)R * WG_XBYTES;            // [T][dY^T hi | dY^T lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(btiles + (size_t)T * b_bytes);
+    uint64_t* raw_full = bars;                 // [R] gathered X rows landed                       (gather -> convert)
+    uint64_t* raw_free = raw_full + R;         // [R] convert warps have read the tile              (convert -> gather)
+    uint64_t* ab_full = raw_free + R;          // [T] X^T hi/lo in TMEM and dY^T hi/lo in smem ready (-> MMA)
+    uint64_t* mma_done = ab_full + T;          // [T] MMAs that read operand stage retired           (MMA -> convert, stager)
+    uint64_t* acc_full = mma_done + T;         // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -69,10 +75,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
     const int nch = min(WG_NCH, p.n_chunks - c_first);          // chunks of this pass (>= 1)
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&empty[s], 1);
-            mbar_init(&raw_full[s], 128);
+        for (int s = 0; s < R; ++s) {
+            mbar_init(&raw_full[s], 128);    // noinc arrive of every gather thread
+            mbar_init(&raw_free[s], 4);
+        }
+        for (int s = 0; s < T; ++s) {
             mbar_init(&ab_full[s], 8);       // 4 convert warps (X^T in TMEM) + 4 stager warps (dY^T in smem)
+            mbar_init(&mma_done[s], 1);
         }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -113,8 +122,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 const int row0 = (rg + t * p.row_groups) * WG_ROWS;
-                mbar_wait_warp(&empty[stage], ph ^ 1, lane);
-                const uint32_t so = (uint32_t)stage * stage_bytes;
+                mbar_wait_warp(&raw_free[stage], ph ^ 1, lane);
+                const uint32_t so = (uint32_t)stage * WG_XBYTES;
                 int idx[16];
                 const bool full = col_ok && row0 + WG_ROWS <= n_out;      // warp-uniform fast path
                 if (full && tbl) {
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[stage]))
                              : "memory");
-                if (++stage == S) { stage = 0; ph ^= 1; }
+                if (++stage == R) { stage = 0; ph ^= 1; }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
         } else if (warp >= 8 && warp < 12) {
@@ -150,23 +159,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             uint32_t xo[8];
 #pragma unroll
             for (int r7 = 0; r7 < 8; ++r7) xo[r7] = swz128(r7, col >> 2) + 4u * (uint32_t)(col & 3);
-            int stage = 0;
-            uint32_t ph = 0;
+            int stage = 0, os = 0;           // raw stage, operand stage
+            uint32_t ph = 0, oph = 0;
             for (int t = 0; t < my_tiles; ++t) {
-                uint8_t* st = tiles + (size_t)stage * stage_bytes;
-                // raw_full fires only after the gather passed `empty` for this round, so the stage's
-                // smem B tiles and TMEM A columns are free to overwrite from here on
                 mbar_wait_warp(&raw_full[stage], ph, lane);
-                const uint32_t a_stage = tmem_base + lane_base + 128u + 128u * (uint32_t)stage;
+                const uint32_t a_stage = tmem_base + lane_base + 128u + 128u * (uint32_t)os;
                 // column `col` of the chunk tile: element (row r, col) sits at swz128(r, col >> 2) + 4 (col & 3)
                 //   = 1024 (r >> 3) + xo[r & 7]: 8 per-thread offsets (hoisted), immediates for the rest
-                const uint32_t xt = smem_u32(st) + cc * WG_XTILE;
+                const uint32_t xt = smem_u32(tiles) + (uint32_t)stage * WG_XBYTES + cc * WG_XTILE;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float v[32], h[32];
 #pragma unroll
                     for (int r = 0; r < 32; ++r)
                         v[r] = cc < nch ? lds_f32(xt + xo[r & 7] + 1024u * (uint32_t)(half * 4 + (r >> 3))) : 0.f;
+                    if (half == 1) {
+                        // both halves are in registers: the raw tile can be refilled
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&raw_free[stage]);
+                    } else {
+                        // the TMEM A stage is free once the MMAs of tile t - T retired
+                        mbar_wait_warp(&mma_done[os], oph ^ 1, lane);
+                        tc_fence_after();
+                    }
 #pragma unroll
                     for (int r = 0; r < 32; ++r) h[r] = __uint_as_float(__float_as_uint(v[r]) & 0xffffe000u);
                     tmem_st32(a_stage + half * 32, h);
@@ -177,8 +192,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ab_full[stage]);
-                if (++stage == S) { stage = 0; ph ^= 1; }
+                if (lane == 0) mbar_arrive(&ab_full[os]);
+                if (++stage == R) { stage = 0; ph ^= 1; }
+                if (++os == T) { os = 0; oph ^= 1; }
             }
         } else if (warp == 12) {
             // ===================== MMA issuer =====================
@@ -186,15 +202,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) |
                                    ((uint32_t)(128 >> 4) << 24);
             const uint32_t tbase = uniform(tmem_base);
-            const uint32_t tiles_u32 = uniform(smem_u32(tiles));
-            const uint32_t bars_u32 = uniform(smem_u32(bars));
+            const uint32_t tiles_u32 = uniform(smem_u32(btiles));
+            const uint32_t bars_u32 = uniform(smem_u32(mma_done));
             const uint32_t desc_hi = (uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
             int stage = 0;
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 mbar_wait_warp(&ab_full[stage], ph, lane);
                 tc_fence_after();
-                const uint32_t b_hi = tiles_u32 + (uint32_t)stage * stage_bytes + WG_XBYTES;
+                const uint32_t b_hi = tiles_u32 + (uint32_t)stage * b_bytes;
                 const uint32_t b_lo = b_hi + 2 * b_tile;
                 const uint32_t a_hi = tbase + 128u + 128u * (uint32_t)stage;
                 const uint32_t empty_bar = bars_u32 + (uint32_t)stage * 8;
@@ -213,7 +229,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                                  : "memory");
                 }
                 __syncwarp();
-                if (++stage == S) { stage = 0; ph ^= 1; }
+                if (++stage == T) { stage = 0; ph ^= 1; }
             }
             if (elect_one()) tc_commit(acc_full);
             __syncwarp();
@@ -230,8 +246,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                 uint32_t ph = 0;
                 for (int t = 0; t < my_tiles; ++t) {
                     const int row0 = (rg + t * p.row_groups) * WG_ROWS;
-                    const uint32_t bh = smem_u32(tiles) + (uint32_t)stage * stage_bytes + WG_XBYTES;
-                    mbar_wait_warp(&empty[stage], ph ^ 1, lane);     // MMAs that read this stage's B tiles retired
+                    const uint32_t bh = smem_u32(btiles) + (uint32_t)stage * b_bytes;
+                    mbar_wait_warp(&mma_done[stage], ph ^ 1, lane);  // MMAs that read this stage's B tiles retired
                     int co = tid % p.Cout, pc = tid / p.Cout;
                     const int dpc = 128 / p.Cout, dco = 128 - dpc * p.Cout;
                     for (int it = tid; it < n_items; it += 128) {
@@ -257,7 +273,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> tensor core
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ab_full[stage]);
-                    if (++stage == S) { stage = 0; ph ^= 1; }
+                    if (++stage == T) { stage = 0; ph ^= 1; }
                 }
             }
             // ===================== epilogue: D[lane m][co] -> dW[co][m] (coalesced fp32 reductions) ==========
@@ -319,13 +335,18 @@ extern "C" int gp_conv_wgrad_tc(const float* X, int ldx, int Cin, const float* d
     if (rgs < 1) rgs = 1;
     if (rgs > n_rt_est) rgs = n_rt_est;
     p.row_groups = rgs;
-    const size_t stage_bytes = WG_XBYTES + (size_t)Cout * 512;
+    // operand ring: 3 stages (tensor memory: D 128 columns + 3 x 128 A columns), 2 when the dY^T tiles are wide;
+    // raw ring: whatever shared memory is left, 2..6 tiles of 32 KB
+    const size_t b_bytes = (size_t)Cout * 512;
     const size_t budget = 227 * 1024, fixed = 1024 + 512;
-    int S = (int)((budget - fixed) / stage_bytes);
-    if (S > 3) S = 3;               // TMEM: D 128 columns + 3 x 128 A columns
-    GP_CHECK_ARG(S >= 2, "gp_conv_wgrad_tc: not enough shared memory for Cout=%d", Cout);
-    p.stages = S;
-    const size_t smem = fixed + (size_t)S * stage_bytes;
+    int T = 3;
+    if (fixed + 3 * b_bytes + 3 * (size_t)WG_XBYTES > budget) T = 2;
+    int R = (int)((budget - fixed - (size_t)T * b_bytes) / WG_XBYTES);
+    if (R > 6) R = 6;
+    GP_CHECK_ARG(R >= 2, "gp_conv_wgrad_tc: not enough shared memory for Cout=%d", Cout);
+    p.raw_stages = R;
+    p.op_stages = T;
+    const size_t smem = fixed + (size_t)R * WG_XBYTES + (size_t)T * b_bytes;
     static thread_local bool configured = false;
     if (!configured) {
         GP_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
