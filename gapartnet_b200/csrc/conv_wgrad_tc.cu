@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
     uint64_t* mma_done = ab_full + T;          // [T] MMAs that read operand stage retired           (MMA -> convert, stager)
     uint64_t* acc_full = mma_done + T;         // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    volatile uint32_t* s_mask = tmem_slot + 2;    // [R][4] bit i: rows 4i..4i+3 of the chunk tile were gathered
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pass = blockIdx.x % p.passes, rg = blockIdx.x / p.passes;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
 
     if (tid == 0) {
         for (int s = 0; s < R; ++s) {
-            mbar_init(&raw_full[s], 128);    // noinc arrive of every gather thread
+            mbar_init(&raw_full[s], 132);    // noinc arrive of every gather thread + one releasing arrive per gather warp
             mbar_init(&raw_free[s], 4);
         }
         for (int s = 0; s < T; ++s) {
@@ -105,19 +106,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
     if (my_tiles > 0) {
         if (warp >= 4 && warp < 8) {
             // ===================== gather X rows of the pass's chunks =====================
-            const int gt = tid - 128;
-            const int j = gt & 7, cc = (gt >> 3) & 3, rq = gt >> 5;      // piece, chunk in pass, row quarter
+            // warp = one chunk tile (32 of the 128 (tap,ci) columns), lane = (16-byte piece j, row rs of a 4-row
+            // group); copy i covers rows 4i .. 4i+3.  LDGSTS.128 costs ~30 cycles per warp instruction no matter
+            // how many lanes fetch (tests/micro/gather_bw.cu), and 58 % of the (row, tap) pairs are absent with
+            // strong spatial coherence - so a group whose 32 lanes are all absent issues NO copy; the bit mask of
+            // the issued groups tells the convert warp which rows to read (the others are zeros).
+            const int cc = warp - 4;
+            const int j = lane & 7, rs = lane >> 3;
             const int kk = (c_first + cc) * 32 + 4 * j;                   // GEMM-M index of this piece
             const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
             const bool col_ok = cc < nch && tap < p.Ktaps;
-            // address arithmetic hoisted out of the tile loop (the kernel is issue bound: ncu counted 7.5 k warp
+            // address arithmetic hoisted out of the tile loop (the kernel was issue bound: ncu counted 7.5 k warp
             // instructions per 64-row tile before this): one 64-bit table pointer and one 32x32->64 multiply-add per
-            // copy; destination of copy i = tile + swz128(rq + 4 i, j) = d_even/d_odd + 1024 (i >> 1)
+            // copy; destination of copy i = tile + swz128(4 i + rs, j) = d_even/d_odd + 1024 (i >> 1)
             const char* Xc = reinterpret_cast<const char*>(p.X) + (size_t)ci * 4;
             const uint32_t ld_bytes = (uint32_t)p.ldx * 4u;
-            const int* tbl = p.nbr ? p.nbr + (size_t)tap * p.tbl_stride + rq : nullptr;
-            const uint32_t d_even = smem_u32(tiles) + cc * WG_XTILE + swz128(rq, j);
-            const uint32_t d_odd = smem_u32(tiles) + cc * WG_XTILE + swz128(rq + 4, j);
+            const int* tbl = p.nbr ? p.nbr + (size_t)tap * p.tbl_stride + rs : nullptr;
+            const uint32_t d_even = smem_u32(tiles) + cc * WG_XTILE + swz128(rs, j);
+            const uint32_t d_odd = smem_u32(tiles) + cc * WG_XTILE + swz128(rs + 4, j);
             int stage = 0;
             uint32_t ph = 0;
             for (int t = 0; t < my_tiles; ++t) {
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                 mbar_wait_warp(&raw_free[stage], ph ^ 1, lane);
                 const uint32_t so = (uint32_t)stage * WG_XBYTES;
                 int idx[16];
-                const bool full = col_ok && row0 + WG_ROWS <= n_out;      // warp-uniform fast path
+                const bool full = col_ok && row0 + WG_ROWS <= n_out;      // fast path (uniform except the last chunk)
                 if (full && tbl) {
                     const int* tp = tbl + row0;
 #pragma unroll
@@ -133,21 +139,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int row = row0 + rq + 4 * i;
+                        const int row = row0 + rs + 4 * i;
                         idx[i] = -1;
                         if (col_ok && row < n_out) idx[i] = tbl ? __ldg(tbl + row0 + 4 * i) : row;
                     }
                 }
+                uint32_t mask = 0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const char* src = Xc + (uint64_t)(uint32_t)(idx[i] >= 0 ? idx[i] : 0) * ld_bytes;
-                    const uint32_t nbytes = idx[i] >= 0 ? 16u : 0u;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                                     ((i & 1) ? d_odd : d_even) + so + 1024u * (i >> 1)),
-                                 "l"(src), "r"(nbytes));
+                    if (__any_sync(0xffffffffu, idx[i] >= 0)) {
+                        const char* src = Xc + (uint64_t)(uint32_t)(idx[i] >= 0 ? idx[i] : 0) * ld_bytes;
+                        const uint32_t nbytes = idx[i] >= 0 ? 16u : 0u;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                                         ((i & 1) ? d_odd : d_even) + so + 1024u * (i >> 1)),
+                                     "l"(src), "r"(nbytes));
+                        mask |= 1u << i;
+                    }
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[stage]))
                              : "memory");
+                if (lane == 0) {
+                    s_mask[stage * 4 + cc] = mask;
+                    mbar_arrive(&raw_full[stage]);      // release: orders the mask store before the phase completes
+                }
                 if (++stage == R) { stage = 0; ph ^= 1; }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
@@ -167,12 +181,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
                 // column `col` of the chunk tile: element (row r, col) sits at swz128(r, col >> 2) + 4 (col & 3)
                 //   = 1024 (r >> 3) + xo[r & 7]: 8 per-thread offsets (hoisted), immediates for the rest
                 const uint32_t xt = smem_u32(tiles) + (uint32_t)stage * WG_XBYTES + cc * WG_XTILE;
+                const uint32_t gmask = cc < nch ? s_mask[stage * 4 + cc] : 0u;     // warp-uniform
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float v[32], h[32];
 #pragma unroll
                     for (int r = 0; r < 32; ++r)
-                        v[r] = cc < nch ? lds_f32(xt + xo[r & 7] + 1024u * (uint32_t)(half * 4 + (r >> 3))) : 0.f;
+                        v[r] = ((gmask >> (half * 8 + (r >> 2))) & 1u)
+                                   ? lds_f32(xt + xo[r & 7] + 1024u * (uint32_t)(half * 4 + (r >> 3)))
+                                   : 0.f;
                     if (half == 1) {
                         // both halves are in registers: the raw tile can be refilled
                         __syncwarp();
