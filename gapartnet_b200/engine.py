@@ -141,6 +141,8 @@ class SparseUNetEngine:
         self._packs: List[tuple] = []
         # grid counters of the split-K convs' in-kernel output zeroing (main stream only; re-armed by each launch)
         self._zero_sync = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._zero_sync_side = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.overlap_fwd = os.environ.get("GAPART_OVERLAP_FWD", "1") != "0"
         self._pack_descs = None
         self._build()
 
@@ -410,9 +412,36 @@ class SparseUNetEngine:
         L = x.level
         if isinstance(blk.shortcut, nn.Identity):
             skip = x
+            h = self._unit_conv_bn(x, blk.conv1[0], blk.conv1[1], L, "subm3", relu=True)
         else:
+            # the 1x1 shortcut conv + BN only meets the main branch at conv2's BatchNorm: its forward runs on the
+            # side stream next to conv1 (fork after x, join before conv2; backward stays serial: both branches
+            # accumulate into the same input gradient)
             skip = self._unit_conv_bn(x, blk.shortcut[0], blk.shortcut[1], L, "k1", relu=False)
-        h = self._unit_conv_bn(x, blk.conv1[0], blk.conv1[1], L, "subm3", relu=True)
+            op = self._fwd.pop()
+            ev_x, ev_skip = torch.cuda.Event(), torch.cuda.Event()
+            eng = self
+
+            def side_op():
+                if not eng.overlap_fwd:
+                    return op()
+                if eng._side_obj is None:
+                    eng._side_obj = torch.cuda.Stream(device=eng.dev)
+                main, side = torch.cuda.current_stream(), eng._side_obj
+                ev_x.record(main)
+                side.wait_event(ev_x)
+                saved = (eng._cur_stream, eng._zero_sync)
+                eng._cur_stream, eng._zero_sync = side.cuda_stream, eng._zero_sync_side
+                try:
+                    with torch.cuda.stream(side):
+                        op()
+                        ev_skip.record(side)
+                finally:
+                    eng._cur_stream, eng._zero_sync = saved
+
+            self._fwd.append(side_op)
+            h = self._unit_conv_bn(x, blk.conv1[0], blk.conv1[1], L, "subm3", relu=True)
+            self._fwd.append(lambda: torch.cuda.current_stream().wait_event(ev_skip) if eng.overlap_fwd else None)
         return self._unit_conv_bn(h, blk.conv2[0], blk.conv2[1], L, "subm3", relu=True, residual=skip, into=into)
 
     def _ublock(self, ub: nn.Module, x: _Act) -> _Act:
