@@ -59,21 +59,25 @@ def test_dense_scene_stress_properties(cuda):
     p_of = par.gather(0, k_of[None].long())[0]
     assert torch.equal(child[k_of.long(), p_of.long()], i)
 
-    # forward / backward: finite, non-trivial, and repeatable up to the fp32 atomics' order noise
-    grads = []
+    # forward / backward: finite, non-trivial, repeatable.  The forward is repeatable to fp32 rounding (measured 8e-7).
+    # The gradients carry the order noise of the fp32 reductions of the split-K convs, amplified by BatchNorm
+    # backward over the ~30 rows of the deepest level of this 2-scene batch (measured 0.7e-3 .. 2.5e-3 of the largest
+    # gradient, with or without the stream overlaps; tests/debug_repeat.py) - the bound only catches gross races.
+    grads, feats = [], []
     for _ in range(2):
         eng.zero_grad()
         f = eng.run_forward()
         assert torch.isfinite(f).all() and float(f.abs().mean()) > 1e-3
+        feats.append(f.clone())
         eng.d_pc_feature.copy_(torch.sin(torch.arange(f.numel(), device=cuda, dtype=torch.float32)).view_as(f) * 1e-3)
         eng.run_backward()
         torch.cuda.synchronize()
         g = eng.flat_grad.clone()
         assert torch.isfinite(g).all() and float(g.abs().max()) > 0
         grads.append(g)
-        # the second forward would advance BatchNorm's running statistics again - irrelevant for the gradients
+    assert float((feats[0] - feats[1]).abs().max()) / float(feats[0].abs().max()) < 1e-5
     denom = float(grads[0].abs().max())
-    assert float((grads[0] - grads[1]).abs().max()) / denom < 1e-4
+    assert float((grads[0] - grads[1]).abs().max()) / denom < 2e-2
 
 
 def test_full_size_tensor_core_path_within_tolerance(cuda):
