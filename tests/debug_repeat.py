@@ -29,5 +29,9 @@ o = 0; worst = []
 for k, nn in names:
     a, b = outs[0][1][o:o + nn], outs[1][1][o:o + nn]
     worst.append((float((a - b).abs().max()) / (float(b.abs().max()) + 1e-30), k)); o += nn
+d = dict((k, v) for v, k in worst)
+for k in ('ublock.decoder_blocks.1.conv2.1.bias', 'ublock.decoder_blocks.1.conv2.1.weight', 'ublock.decoder_blocks.1.conv2.0.weight',
+          'ublock.decoder_blocks.1.conv1.0.weight', 'ublock.decoder_blocks.0.conv2.0.weight', 'stem.0.weight'):
+    print('%-45s run-to-run rel diff %.3e' % (k, d[k]))
 worst.sort(reverse=True)
-print(worst[:6])
+print(worst[:4])
