@@ -8,7 +8,7 @@
 //               convert thread that owns TMEM lane n reads column n of the tile (a warp reads one
 //               contiguous 128-byte row per LDS - conflict free), splits hi/lo and issues tcgen05.st.
 //               No transposed copy is ever stored in shared memory.
-//   B = dY^T  : small K-major smem tile [Cout][64 rows] (hi | lo), written by the convert warps.
+//   B = dY^T  : small K-major smem tile [Cout][64 rows] (hi | lo), written by the stager warps.
 //   D         : fp32 in TMEM; lane m holds dW[:, m]: the epilogue's reductions into the KRSC weight
 //               gradient [Cout][K][Cin] are coalesced across lanes.
 // (An MN-major TF32 smem operand - which would let the tensor core read the gather tile directly -
@@ -17,7 +17,13 @@
 // tiles; partial slices are combined with fp32 red.global.  3xTF32: D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
 //
 // Warp roles (416 threads, 1 CTA/SM): 4 dY^T stagers (-> smem B operand; they run the epilogue after the last
-// tile) | 4 gather (cp.async, zero-fill, noinc barrier) | 4 convert (X^T -> TMEM) | 1 MMA issuer (elected lane).
+// tile) | 4 gather (cp.async, zero-fill, noinc barrier; one warp per 32-column chunk tile, 4-row groups with no
+// present neighbour are skipped and flagged in a bit mask) | 4 convert (X^T -> TMEM) | 1 MMA issuer (elected lane).
+// Two rings: gathered tiles (2..6 x 32 KB, gather -> convert) and operands (TMEM A stage + dY^T tiles, <= 3 stages).
+// Measured history of this kernel (profiles/r1_summary.md): SIMT 261 us -> 105 (first tcgen05 version) -> 97 (dY^T
+// staging on the idle epilogue warps) -> 74 (address arithmetic: the kernel was issue bound) -> 70 us (group skipping)
+// for the L0 16->16 layer; an LDG+STS gather, a second convert group (17 warps: register spills) and a deeper
+// gather ring did not help: LDGSTS rate and the convert chain both sit at ~2 k cycles per stage.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
