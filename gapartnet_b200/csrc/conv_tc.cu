@@ -147,6 +147,7 @@ struct TcParams {
     int ksplit;      // >1: the GEMM-K (chunk) axis of a row tile is split over CTAs, partial tiles are added atomically
     int idx_bulk;    // 1: a tile's neighbour indices arrive as Ktaps cp.async.bulk copies (16-byte aligned table)
     uint32_t inv_cin;  // floor(2^32 / Cin) + 1: kk / Cin == umulhi(kk, inv_cin) for kk < 2^16
+    int ns_feed, ns_mma;   // nanosleep back-off of the feeder / MMA waits (perf experiments: GAPART_TC_NS=feed,mma)
     int* zero_sync;  // != NULL: split-K launch zeroes its own output rows (epilogue warps, before the first reduction)
                      // and synchronises the grid through these two counters {zeroed CTAs, finished CTAs}
     long long* ts;   // optional timestamp trace [6][256] of CTA 0 (perf experiments)
@@ -325,7 +326,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
             const uint32_t sa = (uint32_t)grp + TC_GROUPS * slot;
             if (quad == 1) TC_TS(0, tn);
             // the TMEM stage is free once the MMAs of the chunk that used it last retired
-            mbar_wait_warp(&st_free[sa], (round & 1) ^ 1, lane);
+            if (lane == 0) mbar_wait_sleep(&st_free[sa], (round & 1) ^ 1, (uint32_t)p.ns_feed);
+            __syncwarp();
             tc_fence_after();
             if (quad == 1) TC_TS(1, tn);
             const uint32_t t_stage = t_quad + sa * 64u;
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                         const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_hi + ks * 32) >> 4) & 0x3FFF);
                         const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_lo + ks * 32) >> 4) & 0x3FFF);
                         if (ks == 3 && more) {
-                            mbar_wait_addr(next_bar, pn);
+                            mbar_wait_sleep(&st_full[sn], pn, (uint32_t)p.ns_mma);
                             tc_fence_after();
                         }
                         tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, (c > c0 || ks > 0) ? 1u : 0u);
@@ -822,6 +824,12 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
     p.ksplit = ksplit;
     p.idx_bulk = (nbr != nullptr && (reinterpret_cast<size_t>(nbr) & 15) == 0 && (tbl_stride % 4) == 0) ? 1 : 0;
     int launches = prepacked ? 1 : 2;
+    p.ns_feed = 32;
+    p.ns_mma = 20;
+    {
+        const char* e = getenv("GAPART_TC_NS");
+        if (e) sscanf(e, "%d,%d", &p.ns_feed, &p.ns_mma);
+    }
     p.zero_sync = nullptr;
     if (ksplit > 1) {
         if (!accumulate && zero_sync) {
