@@ -25,3 +25,28 @@ def test_signatures_are_plain_c():
         assert ret in ("int", "long long", "const char*"), (name, ret)
         for t in ptypes:
             assert t in _lib._CT, (name, t)
+
+
+def test_pack_descriptor_layout_matches_header():
+    """GpPackDesc (include/gapart_b200.h, csrc/conv_tc.cu static_assert 72 bytes) as the engine builds it"""
+    import numpy as np
+
+    dt = np.dtype([("W", "<u8"), ("out", "<u8"), ("w_sk", "<i8"), ("w_sci", "<i8"), ("w_sco", "<i8"),
+                   ("flip", "<i4"), ("K", "<i4"), ("Cin", "<i4"), ("Cout", "<i4"), ("n_chunks", "<i4"),
+                   ("cin_real", "<i4"), ("t0", "<i8")])
+    assert dt.itemsize == 72
+    assert [dt.fields[k][1] for k in ("W", "out", "w_sk", "flip", "cin_real", "t0")] == [0, 8, 16, 40, 60, 64]
+
+
+def test_chunk_k_permutation_is_a_bijection():
+    """tc_kperm (csrc/conv_tc.cu): TMEM column -> source float of a 32-float chunk, as tcgen05.st.16x256b lays
+    out a thread's two 16-byte pieces; the weight packer applies the same map, so it must be a permutation."""
+    def kperm(col):
+        n, q, e = col >> 3, (col >> 1) & 3, col & 1
+        return (16 if (n & 2) else 0) + 4 * q + 2 * (n & 1) + e
+
+    assert sorted(kperm(c) for c in range(32)) == list(range(32))
+    # a thread (q) owns floats 4q..4q+3 of the left half and 16+4q..16+4q+3 of the right half
+    for q in range(4):
+        cols = [8 * n + 2 * q + e for n in range(4) for e in range(2)]
+        assert sorted(kperm(c) for c in cols) == [4 * q + i for i in range(4)] + [16 + 4 * q + i for i in range(4)]
