@@ -168,6 +168,171 @@ extern "C" int gp_cluster(const float* points, int p_stride, int N, const int* b
 }
 
 // ---------------------------------------------------------------------------------------------
+// grid-accelerated fused clustering.  The brute-force scan above is O(Q * N / B): 320 k queries x 20 k points took
+// ~100 ms of the 128 ms full train step (profiles/r1_summary.md).  A uniform grid with cells slightly larger than
+// the radius confines the candidates of a query to 27 cells.  Exactness of the TRUNCATED semantics ("first `cap`
+// hits in ascending point index") is kept without sorting: a query with at most `cap` hits in total unions all of
+// them (order irrelevant for the components); only a query with more hits falls back to the ordered scan.
+// ---------------------------------------------------------------------------------------------
+#include <cub/device/device_scan.cuh>
+
+#define CG 64                               // cells per axis and scene (coordinates beyond are clamped: monotone)
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__global__ void k_cg_min(const float4* __restrict__ pts, int n, unsigned* __restrict__ mn) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned x = 0xffffffffu, y = 0xffffffffu, z = 0xffffffffu;
+    if (i < n) {
+        float4 p = pts[i];
+        x = f2ord(p.x); y = f2ord(p.y); z = f2ord(p.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x = min(x, __shfl_xor_sync(0xffffffffu, x, o));
+        y = min(y, __shfl_xor_sync(0xffffffffu, y, o));
+        z = min(z, __shfl_xor_sync(0xffffffffu, z, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mn + 0, x); atomicMin(mn + 1, y); atomicMin(mn + 2, z);
+    }
+}
+__device__ __forceinline__ int3 cg_cell(float4 p, const unsigned* mn, float inv_cell) {
+    int3 c;
+    c.x = min(max((int)floorf((p.x - ord2f(mn[0])) * inv_cell), 0), CG - 1);
+    c.y = min(max((int)floorf((p.y - ord2f(mn[1])) * inv_cell), 0), CG - 1);
+    c.z = min(max((int)floorf((p.z - ord2f(mn[2])) * inv_cell), 0), CG - 1);
+    return c;
+}
+__global__ void k_cg_count(const float4* __restrict__ pts, const int* __restrict__ batch_indices, int n,
+                           const unsigned* __restrict__ mn, float inv_cell, int* __restrict__ keys,
+                           int* __restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int3 c = cg_cell(pts[i], mn, inv_cell);
+    int key = ((batch_indices[i] * CG + c.x) * CG + c.y) * CG + c.z;
+    keys[i] = key;
+    atomicAdd(counts + key, 1);
+}
+__global__ void k_cg_fill(const int* __restrict__ keys, int n, const int* __restrict__ starts, int* __restrict__ counts,
+                          int* __restrict__ order) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int key = keys[i];
+    int c = atomicAdd(counts + key, -1);        // counts down to 0: slot c-1 of the cell
+    order[starts[key] + c - 1] = i;
+}
+__global__ void __launch_bounds__(128) k_cg_cluster(const float4* __restrict__ pts, const int* __restrict__ batch_indices,
+                                                    const int* __restrict__ batch_offsets, int Q, float radius2, int cap,
+                                                    int use_labels, const unsigned* __restrict__ mn, float inv_cell,
+                                                    const int* __restrict__ starts, const int* __restrict__ order,
+                                                    int* __restrict__ num, int* __restrict__ parent) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const float4 c = pts[q];
+    const int b = batch_indices[q];
+    const int lab = __float_as_int(c.w);
+    const int3 cc = cg_cell(c, mn, inv_cell);
+    const int x0 = max(cc.x - 1, 0), x1 = min(cc.x + 1, CG - 1);
+    const int y0 = max(cc.y - 1, 0), y1 = min(cc.y + 1, CG - 1);
+    const int z0 = max(cc.z - 1, 0), z1 = min(cc.z + 1, CG - 1);
+    int tot = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        // pass 0 counts the hits; pass 1 (only when nothing is truncated) unions them
+        for (int x = x0; x <= x1; ++x)
+            for (int y = y0; y <= y1; ++y) {
+                // the z-run of a (x, y) column is contiguous in the cell order: one range per column
+                const int key0 = ((b * CG + x) * CG + y) * CG + z0;
+                const int jb = starts[key0], je = starts[key0 + (z1 - z0) + 1];
+                for (int j = jb; j < je; ++j) {
+                    const int k = order[j];
+                    const float4 p = __ldg(pts + k);
+                    if (use_labels && __float_as_int(p.w) != lab) continue;
+                    // same expression as the ordered scan (k_ball_query): bit-identical radius test
+                    float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+                    float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    if (d2 < radius2) {
+                        if (pass == 0) ++tot; else uf_union(parent, q, k);
+                    }
+                }
+            }
+        if (tot > cap) break;
+    }
+    if (tot > cap) {
+        // truncated query: the first `cap` hits in ascending point index decide the edges -> ordered scan
+        const int s = batch_offsets[b], e = batch_offsets[b + 1];
+        int cnt = 0;
+        for (int k = s; k < e && cnt < cap; ++k) {
+            const float4 p = __ldg(pts + k);
+            if (use_labels && __float_as_int(p.w) != lab) continue;
+            float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 < radius2) {
+                uf_union(parent, q, k);
+                ++cnt;
+            }
+        }
+        tot = cap;
+    }
+    if (num) num[q] = tot;
+}
+
+static long long cg_cells(int batch) { return (long long)batch * CG * CG * CG; }
+
+extern "C" long long gp_cluster_grid_ws_ints(int N, int batch) {
+    size_t temp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp, (const int*)nullptr, (int*)nullptr, (int)(cg_cells(batch) + 1));
+    return 2ll * N + 2 * (cg_cells(batch) + 1) + 8 + (long long)((temp + 3) / 4) + 128;   // + 256-byte alignment slack
+}
+
+// gp_cluster with a uniform grid (same results, bit for bit); ws: gp_cluster_grid_ws_ints(N, batch) ints
+extern "C" int gp_cluster_grid(const float* points, int p_stride, int N, const int* batch_indices,
+                               const int* batch_offsets, int batch, float radius, int num_samples, const int* labels,
+                               float* pts4_ws, int* ws, long long ws_ints, int* cc_labels, int* num_points_per_query,
+                               void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(num_samples > 0 && p_stride >= 3 && batch > 0 && radius > 0.f, "gp_cluster_grid: bad arguments");
+    GP_CHECK_ARG(cg_cells(batch) < (1ll << 30), "gp_cluster_grid: batch too large for the cell directory");
+    if (N == 0) return GP_OK;
+    const long long cells = cg_cells(batch);
+    size_t temp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp, (const int*)nullptr, (int*)nullptr, (int)(cells + 1));
+    GP_CHECK_ARG(ws_ints >= 2ll * N + 2 * (cells + 1) + 8 + (long long)((temp + 3) / 4) + 128,
+                 "gp_cluster_grid: workspace too small");
+    int* keys = ws;
+    int* order = keys + N;
+    int* counts = order + N;
+    int* starts = counts + (cells + 1);
+    unsigned* mn = reinterpret_cast<unsigned*>(starts + (cells + 1));
+    void* cub_tmp = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(mn + 8) + 255) & ~(uintptr_t)255);
+    const int g = gp_cdiv(N, 256);
+    // cells 0.1 % larger than the radius: two points closer than the radius are at most one cell apart per axis
+    // even after the fp32 rounding of (x - min) / cell
+    const float inv_cell = 1.0f / (radius * 1.001f);
+    k_pack_xyzl<<<g, 256, 0, stream>>>(points, p_stride, labels, N, (float4*)pts4_ws);
+    k_iota<<<g, 256, 0, stream>>>(cc_labels, N);
+    GP_CUDA(cudaMemsetAsync(mn, 0xff, 3 * sizeof(unsigned), stream));
+    GP_CUDA(cudaMemsetAsync(counts, 0, (size_t)(cells + 1) * sizeof(int), stream));
+    k_cg_min<<<g, 256, 0, stream>>>((const float4*)pts4_ws, N, mn);
+    k_cg_count<<<g, 256, 0, stream>>>((const float4*)pts4_ws, batch_indices, N, mn, inv_cell, keys, counts);
+    GP_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, temp, counts, starts, (int)(cells + 1), stream));
+    k_cg_fill<<<g, 256, 0, stream>>>(keys, N, starts, counts, order);
+    k_cg_cluster<<<gp_cdiv(N, 128), 128, 0, stream>>>((const float4*)pts4_ws, batch_indices, batch_offsets, N,
+                                                      radius * radius, num_samples, labels != nullptr, mn, inv_cell,
+                                                      starts, order, num_points_per_query, cc_labels);
+    k_ccl_flatten<<<g, 256, 0, stream>>>(cc_labels, N);
+    gp_note_launch(8);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // segmented reductions: x [N, C], segments [begin[s], end[s]) -> out [S, C]
 // mode 0 sum, 1 min, 2 max (argmax optional for max)
 // ---------------------------------------------------------------------------------------------

@@ -209,6 +209,13 @@ int gp_ccl(const int* offsets_flat, const int* edges_flat, int num_vertices, int
 int gp_cluster(const float* points, int p_stride, int N, const int* batch_indices,
                const int* batch_offsets, float radius, int num_samples, const int* labels,
                float* pts4_ws, int* cc_labels, int* num_points_per_query, void* stream);
+/* gp_cluster through a uniform grid (cell = 1.001 * radius, 64^3 cells per scene, candidates from 27 cells): the same
+ * labels bit for bit - a query with at most num_samples hits unions all of them, a truncated one falls back to the
+ * ordered scan.  batch = number of scenes; ws: gp_cluster_grid_ws_ints(N, batch) ints. */
+long long gp_cluster_grid_ws_ints(int N, int batch);
+int gp_cluster_grid(const float* points, int p_stride, int N, const int* batch_indices, const int* batch_offsets,
+                    int batch, float radius, int num_samples, const int* labels, float* pts4_ws, int* ws,
+                    long long ws_ints, int* cc_labels, int* num_points_per_query, void* stream);
 
 /* epic_ops.reduce.segmented_reduce(x, begin, end, mode) / segmented_maxpool(x, begin, end)
  * (gapartnet/network/grouping_utils.py:59-70, network/model.py:360-362). mode 0 sum, 1 min, 2 max;

@@ -142,3 +142,24 @@ def test_nms_matches_greedy(cuda):
     ref = oc.nms(ious, scores, 0.7)
     np.testing.assert_array_equal(keep.cpu().numpy(), ref)
     assert 0 < ref.shape[0] < P
+
+
+@pytest.mark.parametrize("cap,radius,scale", [(50, 0.08, 1.0), (300, 0.08, 1.0), (6, 0.08, 1.0), (50, 0.03, 1.0), (20, 0.08, 5.0), (50, 0.01, 1.0)])
+def test_grid_cluster_is_bit_identical_to_the_ordered_scan(cuda, cap, radius, scale):
+    """gp_cluster_grid (27-cell candidate search; truncated queries fall back to the ordered scan) against the
+    O(Q*N/B) scan and the oracle: labels and per-query counts bit for bit, with heavy truncation (cap 6), a small
+    radius, and coordinates far outside the 64-cell box (clamped border cells)."""
+    xyz, sem, bidx, off = _scene_points(batch=3, n=4000, seed=21)
+    xyz = (xyz * np.float32(scale)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    cc_s, num_s = ccl.cluster(t(xyz), t(bidx), t(off), radius * scale, cap, labels=t(sem), use_grid=False)
+    cc_g, num_g = ccl.cluster(t(xyz), t(bidx), t(off), radius * scale, cap, labels=t(sem), use_grid=True)
+    assert torch.equal(cc_s, cc_g) and torch.equal(num_s, num_g)
+    labels_ref, order_ref = oc.cluster_proposals(xyz, bidx, off, sem, radius * scale, cap)
+    sorted_cc, sorted_idx = torch.sort(cc_g.long(), stable=True)
+    np.testing.assert_array_equal(sorted_cc.cpu().numpy(), labels_ref)
+    np.testing.assert_array_equal(sorted_idx.cpu().numpy(), order_ref)
+    # without labels
+    cc_s, num_s = ccl.cluster(t(xyz), t(bidx), t(off), radius * scale, cap, use_grid=False)
+    cc_g, num_g = ccl.cluster(t(xyz), t(bidx), t(off), radius * scale, cap, use_grid=True)
+    assert torch.equal(cc_s, cc_g) and torch.equal(num_s, num_g)
