@@ -172,7 +172,7 @@ extern "C" int gp_cluster(const float* points, int p_stride, int N, const int* b
 // ~100 ms of the 128 ms full train step (profiles/r1_summary.md).  A uniform grid with cells slightly larger than
 // the radius confines the candidates of a query to 27 cells.  Exactness of the TRUNCATED semantics ("first `cap`
 // hits in ascending point index") is kept without sorting: a query with at most `cap` hits in total unions all of
-// them (order irrelevant for the components); only a query with more hits falls back to the ordered scan.
+// them (order irrelevant for the components); a query with more hits selects the cap smallest hit indices.
 // ---------------------------------------------------------------------------------------------
 #include <cub/device/device_scan.cuh>
 
@@ -227,6 +227,35 @@ __global__ void k_cg_fill(const int* __restrict__ keys, int n, const int* __rest
     int c = atomicAdd(counts + key, -1);        // counts down to 0: slot c-1 of the cell
     order[starts[key] + c - 1] = i;
 }
+#define CG_MAXH 320                         // hit indices a query keeps in local memory (>= the reference's caps 50 / 300)
+
+// visit every candidate of query q (27 cells, label filter, bit-identical radius test of k_ball_query); f(k) per hit
+template <typename F>
+__device__ __forceinline__ void cg_for_hits(const float4* __restrict__ pts, const int* __restrict__ starts,
+                                            const int* __restrict__ order, const float4 c, int b, int lab, int use_labels,
+                                            float radius2, int x0, int x1, int y0, int y1, int z0, int z1, F&& f) {
+    for (int x = x0; x <= x1; ++x)
+        for (int y = y0; y <= y1; ++y) {
+            // the z-run of a (x, y) column is contiguous in the cell order: one range per column
+            const int key0 = ((b * CG + x) * CG + y) * CG + z0;
+            const int jb = starts[key0], je = starts[key0 + (z1 - z0) + 1];
+            for (int j = jb; j < je; ++j) {
+                const int k = order[j];
+                const float4 p = __ldg(pts + k);
+                if (use_labels && __float_as_int(p.w) != lab) continue;
+                float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < radius2) f(k);
+            }
+        }
+}
+
+// One thread per query.  ONE scan of the 27 cells collects the hit indices (local memory, CG_MAXH).  The reference
+// semantics are "the first `cap` hits in ascending point index" (a linear scan that stops at the cap); the edges only
+// depend on that SET, so a truncated query selects the cap smallest indices by bisecting the index threshold over its
+// collected hits (no second distance pass, no O(N/B) ordered scan: that fallback took 42 ms per call when a random-init
+// semantic head predicts one class everywhere and every query overflows cap = 50).  More than CG_MAXH hits (dense
+// scenes): the bisection re-scans the cells instead.
 __global__ void __launch_bounds__(128) k_cg_cluster(const float4* __restrict__ pts, const int* __restrict__ batch_indices,
                                                     const int* __restrict__ batch_offsets, int Q, float radius2, int cap,
                                                     int use_labels, const unsigned* __restrict__ mn, float inv_cell,
@@ -241,42 +270,35 @@ __global__ void __launch_bounds__(128) k_cg_cluster(const float4* __restrict__ p
     const int x0 = max(cc.x - 1, 0), x1 = min(cc.x + 1, CG - 1);
     const int y0 = max(cc.y - 1, 0), y1 = min(cc.y + 1, CG - 1);
     const int z0 = max(cc.z - 1, 0), z1 = min(cc.z + 1, CG - 1);
+    int h[CG_MAXH];
     int tot = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        // pass 0 counts the hits; pass 1 (only when nothing is truncated) unions them
-        for (int x = x0; x <= x1; ++x)
-            for (int y = y0; y <= y1; ++y) {
-                // the z-run of a (x, y) column is contiguous in the cell order: one range per column
-                const int key0 = ((b * CG + x) * CG + y) * CG + z0;
-                const int jb = starts[key0], je = starts[key0 + (z1 - z0) + 1];
-                for (int j = jb; j < je; ++j) {
-                    const int k = order[j];
-                    const float4 p = __ldg(pts + k);
-                    if (use_labels && __float_as_int(p.w) != lab) continue;
-                    // same expression as the ordered scan (k_ball_query): bit-identical radius test
-                    float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
-                    float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    if (d2 < radius2) {
-                        if (pass == 0) ++tot; else uf_union(parent, q, k);
-                    }
-                }
+    cg_for_hits(pts, starts, order, c, b, lab, use_labels, radius2, x0, x1, y0, y1, z0, z1, [&](int k) {
+        if (tot < CG_MAXH) h[tot] = k;
+        ++tot;
+    });
+    if (tot <= cap) {
+        for (int i = 0; i < tot; ++i) uf_union(parent, q, h[i]);
+    } else {
+        // index threshold T = the cap-th smallest hit index: smallest T with #(hits <= T) >= cap
+        int lo = batch_offsets[b], hi = batch_offsets[b + 1] - 1;
+        const bool cached = tot <= CG_MAXH;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int cnt = 0;
+            if (cached) {
+                for (int i = 0; i < tot; ++i) cnt += h[i] <= mid;
+            } else {
+                cg_for_hits(pts, starts, order, c, b, lab, use_labels, radius2, x0, x1, y0, y1, z0, z1,
+                            [&](int k) { cnt += k <= mid; });
             }
-        if (tot > cap) break;
-    }
-    if (tot > cap) {
-        // truncated query: the first `cap` hits in ascending point index decide the edges -> ordered scan
-        const int s = batch_offsets[b], e = batch_offsets[b + 1];
-        int cnt = 0;
-        for (int k = s; k < e && cnt < cap; ++k) {
-            const float4 p = __ldg(pts + k);
-            if (use_labels && __float_as_int(p.w) != lab) continue;
-            float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
-            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (d2 < radius2) {
-                uf_union(parent, q, k);
-                ++cnt;
-            }
+            if (cnt >= cap) hi = mid; else lo = mid + 1;
+        }
+        if (cached) {
+            for (int i = 0; i < tot; ++i)
+                if (h[i] <= lo) uf_union(parent, q, h[i]);
+        } else {
+            cg_for_hits(pts, starts, order, c, b, lab, use_labels, radius2, x0, x1, y0, y1, z0, z1,
+                        [&](int k) { if (k <= lo) uf_union(parent, q, k); });
         }
         tot = cap;
     }
@@ -336,31 +358,69 @@ extern "C" int gp_cluster_grid(const float* points, int p_stride, int N, const i
 // segmented reductions: x [N, C], segments [begin[s], end[s]) -> out [S, C]
 // mode 0 sum, 1 min, 2 max (argmax optional for max)
 // ---------------------------------------------------------------------------------------------
+// One CTA (128 threads) per segment: thread t owns rows b+t, b+t+128, ... (a warp-per-segment serial loop took 1.2 ms per
+// call in the full train step: one proposal can hold a whole scene).  Sums are accumulated in fp64 and rounded to fp32
+// once, so the result does not depend on the summation order (oracle/cluster.py does the same); max keeps the FIRST
+// maximum in ascending row order, whatever thread found it.
+#define SEG_CH 8
 __global__ void __launch_bounds__(128) k_seg_reduce(const float* __restrict__ x, int ldx, int C,
                                                     const int* __restrict__ begin, const int* __restrict__ end,
                                                     int S, int mode, float* __restrict__ out,
                                                     int* __restrict__ argout) {
-    // one warp per (segment, 32-channel slab); lanes own channels (coalesced row reads)
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    int slabs = (C + 31) / 32;
-    if (warp >= S * slabs) return;
-    int s = warp / slabs, c = (warp - s * slabs) * 32 + lane;
-    if (c >= C) return;
-    int b = begin[s], e = end[s];
-    float acc = mode == 0 ? 0.f : (mode == 1 ? FLT_MAX : -FLT_MAX);
-    int arg = -1;
-    for (int r = b; r < e; ++r) {
-        float v = __ldg(x + (size_t)r * ldx + c);
-        if (mode == 0) acc += v;
-        else if (mode == 1) acc = fminf(acc, v);
-        else if (arg < 0 || v > acc) {   // first maximum wins (ascending row order)
-            acc = v;
-            arg = r;
+    __shared__ double s_val[4][SEG_CH];
+    __shared__ int s_arg[4][SEG_CH];
+    const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = begin[s], e = end[s];
+    for (int c0 = 0; c0 < C; c0 += SEG_CH) {
+        const int nc = min(SEG_CH, C - c0);
+        double acc[SEG_CH];
+        int arg[SEG_CH];
+#pragma unroll
+        for (int j = 0; j < SEG_CH; ++j) {
+            acc[j] = mode == 0 ? 0.0 : (mode == 1 ? (double)FLT_MAX : -(double)FLT_MAX);
+            arg[j] = 0x7fffffff;
         }
+        for (int r = b + tid; r < e; r += 128) {
+            const float* row = x + (size_t)r * ldx + c0;
+#pragma unroll
+            for (int j = 0; j < SEG_CH; ++j) {
+                if (j < nc) {
+                    const double v = (double)__ldg(row + j);
+                    if (mode == 0) acc[j] += v;
+                    else if (mode == 1) acc[j] = fmin(acc[j], v);
+                    else if (v > acc[j] || arg[j] == 0x7fffffff) { acc[j] = v; arg[j] = r; }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SEG_CH; ++j) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, acc[j], o);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg[j], o);
+                if (mode == 0) acc[j] += ov;
+                else if (mode == 1) acc[j] = fmin(acc[j], ov);
+                else if (ov > acc[j] || (ov == acc[j] && oa < arg[j])) { acc[j] = ov; arg[j] = oa; }
+            }
+            if (lane == 0) { s_val[warp][j] = acc[j]; s_arg[warp][j] = arg[j]; }
+        }
+        __syncthreads();
+        if (tid < nc) {
+            double v = s_val[0][tid];
+            int a = s_arg[0][tid];
+            for (int w = 1; w < 4; ++w) {
+                const double ov = s_val[w][tid];
+                const int oa = s_arg[w][tid];
+                if (mode == 0) v += ov;
+                else if (mode == 1) v = fmin(v, ov);
+                else if (ov > v || (ov == v && oa < a)) { v = ov; a = oa; }
+            }
+            if (e <= b) { v = 0.0; a = -1; }   // empty segment
+            out[(size_t)s * C + c0 + tid] = (float)v;
+            if (argout) argout[(size_t)s * C + c0 + tid] = (mode == 2 && e > b) ? a : -1;
+        }
+        __syncthreads();
     }
-    if (e <= b && mode != 0) acc = 0.f;   // empty segment
-    out[(size_t)s * C + c] = acc;
-    if (argout) argout[(size_t)s * C + c] = arg;
 }
 
 extern "C" int gp_segmented_reduce(const float* x, int ldx, int C, const int* begin, const int* end, int S,
@@ -368,8 +428,7 @@ extern "C" int gp_segmented_reduce(const float* x, int ldx, int C, const int* be
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(mode >= 0 && mode <= 2 && C > 0, "gp_segmented_reduce: mode must be 0 (sum), 1 (min) or 2 (max)");
     if (S == 0) return GP_OK;
-    long long warps = (long long)S * ((C + 31) / 32);
-    k_seg_reduce<<<gp_cdiv(warps * 32, 128), 128, 0, stream>>>(x, ldx, C, begin, end, S, mode, out, argmax);
+    k_seg_reduce<<<S, 128, 0, stream>>>(x, ldx, C, begin, end, S, mode, out, argmax);
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;

@@ -11,7 +11,7 @@
 // (10-bit mantissa).  We use the 3xTF32 split: a = a_hi + a_lo, b = b_hi + b_lo (hi = top 19 bits),
 //   D += a_hi*b_hi + a_lo*b_hi + a_hi*b_lo          (error ~2^-21, fp32 accumulate in TMEM)
 //
-// Data path of the A operand (third design; measurements in profiles/r1_summary.md, tests/micro/):
+// Data path of the A operand (third design; measurements in profiles/r1_summary.md, tools/micro/):
 //   v1/v2  cp.async(16 B, zero-fill) -> swizzled smem tile -> convert warps (LDS, split) -> TMEM.
 //          An SM sustains only ~1 LDGSTS.128 per 30 cycles (850-1400 cycles per 16 KB chunk with 4-16
 //          gather warps, independent of how many lanes actually fetch), TMA tile::gather4 ~135 cycles per
@@ -20,7 +20,7 @@
 //          own one row, each lane fetches one 16-byte piece of the left and of the right 64-byte half of
 //          the chunk row (170-400 cycles per chunk in the same micro-benchmark) - split hi/lo in place
 //          and store both operands to tensor memory with tcgen05.st.16x256b, whose register<->(lane,
-//          column) map is exactly "4 lanes per row" (tests/micro/tmem_layout.cu).  No shared-memory
+//          column) map is exactly "4 lanes per row" (tools/micro/tmem_layout.cu).  No shared-memory
 //          staging, no LDS, no data barrier between gather and convert; absent neighbours are zeros in
 //          registers.  The price is a fixed permutation of the 32 K positions inside a chunk, which
 //          k_pack_weights applies to the weight images (tc_kperm).
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
             mbar_wait_warp(&acc_empty[buf], acc_ph ^ 1, lane);
             // operands of the first chunk; inside the loop the wait for chunk c+1 is issued between the MMAs
             // of chunk c so that its ~100-cycle latency overlaps the tensor pipe draining its queue (a tf32
-            // MMA of M=128, K=8 occupies the pipe for 10 + N/2 cycles: tests/micro/mma_rate.cu)
+            // MMA of M=128, K=8 occupies the pipe for 10 + N/2 cycles: tools/micro/mma_rate.cu)
             mbar_wait_warp(&st_full[sa], pa, lane);
             tc_fence_after();
             const uint32_t d_tmem = tbase + (uint32_t)buf * accw;

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const WgParams p) {
             // ===================== gather X rows of the pass's chunks =====================
             // warp = one chunk tile (32 of the 128 (tap,ci) columns), lane = (16-byte piece j, row rs of a 4-row
             // group); copy i covers rows 4i .. 4i+3.  LDGSTS.128 costs ~30 cycles per warp instruction no matter
-            // how many lanes fetch (tests/micro/gather_bw.cu), and 58 % of the (row, tap) pairs are absent with
+            // how many lanes fetch (tools/micro/gather_bw.cu), and 58 % of the (row, tap) pairs are absent with
             // strong spatial coherence - so a group whose 32 lanes are all absent issues NO copy; the bit mask of
             // the issued groups tells the convert warp which rows to read (the others are zeros).
             const int cc = warp - 4;

@@ -121,7 +121,7 @@ def voxelize_raw(xyz: torch.Tensor, feats: torch.Tensor, batch_offsets: torch.Te
                   per_scene, *g.shape, _p(g.words), _p(g.prefix), _p(g.scan_tmp()), _p(pt_cell), maxv,
                   _p(vfeat), _p(vcnt), _p(coords4), _p(pcid), _p(d_num), _p(splits), _stream())
     return dict(voxel_feats=vfeat, coords4=coords4, pc_voxel_id=pcid[:N], d_num=d_num,
-                batch_splits=splits, grid=g, max_voxels=maxv)
+                batch_splits=splits, grid=g, max_voxels=maxv, voxel_cnt=vcnt)
 
 
 # ---------------------------------------------------------------------------------------------

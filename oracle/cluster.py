@@ -67,10 +67,9 @@ def segmented_reduce(x, begin, end, mode):
             continue
         seg = x[b:e]
         if mode == "sum":
-            acc = np.zeros(x.shape[1], dtype=np.float32)
-            for r in seg:                       # sequential fp32 accumulation, as the kernel does
-                acc = acc + r
-            out[s] = acc
+            # fp64 accumulation, rounded to fp32 once: independent of the summation order (the kernel
+            # reduces a segment in parallel the same way)
+            out[s] = seg.astype(np.float64).sum(0).astype(np.float32)
         elif mode == "min":
             out[s] = seg.min(0)
         else:

@@ -4,7 +4,7 @@ Provides exactly the names /root/reference/gapartnet/network/backbone.py:2,8-165
 (SparseConvTensor, SparseModule, SparseSequential, SubMConv3d, SparseConv3d, SparseInverseConv3d)
 so that the reference's own backbone.py, or this repo's mirror of it, can run on CPU with torch
 autograd supplying the backward.  Arithmetic: gather rows -> mm with the tap's [Cin,Cout] slice ->
-index_add (fp32), i.e. the textbook gather-GEMM-scatter; `dense_conv3d_check` evaluates the same
+accumulate per output row, i.e. the textbook gather-GEMM-scatter; `dense_conv3d_check` evaluates the same
 layer with torch.nn.functional.conv3d on the densified grid as an independent second opinion.
 Weight layout: [Cout, k0, k1, k2, Cin] (spconv 2.x KRSC; parity unpinned).
 """
@@ -65,14 +65,18 @@ class SparseSequential(SparseModule):
 
 
 def _apply_table(feats, weight_kio, table, n_out):
-    """feats [n_in,Cin], weight_kio [K,Cin,Cout], table [K,n_out] -> [n_out,Cout]"""
-    out = feats.new_zeros((n_out, weight_kio.shape[2]))
+    """feats [n_in,Cin], weight_kio [K,Cin,Cout], table [K,n_out] -> [n_out,Cout].
+    Output stationary: per tap, gather the neighbour rows (absent neighbours read an appended zero row), multiply by
+    the tap's [Cin,Cout] slice, add.  (index_select + mm is ~8x faster than index_add in fp64 on CPU, which is what
+    lets the parity tests run the full 16-scene configuration in fp64.)"""
     t = torch.as_tensor(table, dtype=torch.long)
+    n_in = feats.shape[0]
+    xp = torch.cat([feats, feats.new_zeros((1, feats.shape[1]))])
+    out = feats.new_zeros((n_out, weight_kio.shape[2]))
     for k in range(t.shape[0]):
-        o = torch.nonzero(t[k] >= 0).squeeze(1)
-        if o.numel() == 0:
+        if not bool((t[k] >= 0).any()):
             continue
-        out = out.index_add(0, o, feats[t[k, o]] @ weight_kio[k])
+        out = out + xp.index_select(0, torch.where(t[k] >= 0, t[k], n_in)) @ weight_kio[k]
     return out
 
 

@@ -1,0 +1,133 @@
+"""GPU: the full GAPartNet train step against tests/golden/cfg4_step.npz - outputs of the REFERENCE's own
+`_training_or_validation_step` (network/model.py:466-659 + grouping_utils.py + dataset/gapartnet.py + structure/point_cloud.py,
+imported unmodified by tests/golden/ref_harness.py with the third-party kernels replaced by the CPU oracle; generator:
+tests/golden/make_golden_cfg4.py).  Same synthetic scenes, bit-identical weights (tests/util.deterministic_weights), the
+reference's torch.rand draws injected.
+
+Bars: integer / index outputs bit-exact (semantic arg-max, proposal point sets, CSR offsets, IoU table); floating point
+within the tolerance written next to each check (north_star: logits within 1e-3 relative)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gapartnet_b200 import synthetic
+from gapartnet_b200.network.model import GAPartNet, batch_from_scenes
+
+from util import deterministic_weights, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg4_step.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(GOLD)
+    cfg = json.loads(bytes(g["cfg_json"]).decode())
+    return g, cfg
+
+
+def _model(cuda, cfg):
+    scenes = [synthetic.planes(cfg["seed0"] + b, cfg["points"]) for b in range(cfg["batch"])]
+    net = GAPartNet(channels=cfg["channels"], block_repeat=cfg["block_repeat"]).to(cuda)
+    deterministic_weights(net, cfg["weight_seed"], cfg["gains"])
+    net.attach_engine(batch=cfg["batch"], max_points=cfg["batch"] * cfg["points"], voxel_size=cfg["voxel"],
+                      spatial_shape=(64, 64, 64))
+    net.train()
+    return net, batch_from_scenes(scenes, cuda)
+
+
+def _relL2(a, b):
+    a = torch.as_tensor(a).double().cpu().flatten()
+    b = torch.as_tensor(b).double().cpu().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def test_full_step_matches_the_reference_step(cuda, gold):
+    g, cfg = gold
+    net, batch = _model(cuda, cfg)
+    net.zero_grad()
+    rand = torch.from_numpy(g["rand"]).to(cuda)
+    taps = {}
+    fb, fs, fo = net.forward_backbone, net.forward_sem_seg, net.forward_offset
+    net.forward_backbone = lambda b: taps.setdefault("pc_feature", fb(b))
+    net.forward_sem_seg = lambda f: taps.setdefault("sem_logits", fs(f))
+    net.forward_offset = lambda f: taps.setdefault("offsets", fo(f))
+    out = net.training_step(batch, training_schedule=(0, 0), rand=rand)
+    assert net.engine.level_counts()[0] == int(g["level0_voxels"])
+
+    # dense stage: per-point features / logits / offsets, 1e-3 of the largest magnitude (north_star tolerance)
+    assert rel_err(taps["pc_feature"][::8], torch.from_numpy(g["pc_feature_s8"])) < 1e-3
+    assert rel_err(taps["sem_logits"][::4], torch.from_numpy(g["sem_logits_s4"])) < 1e-3
+    assert rel_err(taps["offsets"], torch.from_numpy(g["offsets"])) < 1e-3
+    sem_preds = taps["sem_logits"].argmax(-1).cpu().numpy()
+    np.testing.assert_array_equal(sem_preds, g["sem_preds"])        # fixture margin between top-2 logits: 3e-3
+    assert abs(float(out["all_accu"]) - float(g["all_accu"])) < 1e-6
+    for k in ("loss_sem_seg", "loss_offset_dist", "loss_offset_dir"):
+        assert abs(float(out[k]) - float(g[k])) <= 1e-3 * max(1.0, abs(float(g[k]))), (k, float(out[k]), float(g[k]))
+
+    # proposal stage: bit-exact index sets
+    p = out["proposals"]
+    np.testing.assert_array_equal(p["valid_mask"].cpu().numpy(), g["valid_mask"])
+    np.testing.assert_array_equal(p["sorted_indices"].cpu().numpy(), g["sorted_indices"])
+    np.testing.assert_array_equal(p["proposal_offsets"].cpu().numpy(), g["proposal_offsets"])
+    np.testing.assert_array_equal(p["proposal_indices"].cpu().numpy(), g["proposal_indices"])
+    np.testing.assert_array_equal(p["sem_preds"].cpu().numpy(), g["prop_sem_preds"])
+    np.testing.assert_array_equal(p["instance_labels"].cpu().numpy(), g["prop_instance_labels"])
+    np.testing.assert_array_equal(p["ious"].cpu().numpy(), g["ious"])
+    # score / NPCS branch (two 2-level sparse U-Nets on the re-voxelised proposals): 2e-3 relative
+    assert rel_err(p["score_preds"], torch.from_numpy(g["score_preds"])) < 2e-3
+    for k in ("loss_prop_score", "loss_prop_npcs", "loss"):
+        assert abs(float(out[k]) - float(g[k])) <= 2e-3 * abs(float(g[k])), (k, float(out[k]), float(g[k]))
+
+    out["loss"].backward()
+    params = dict(net.named_parameters())
+    for key in g.files:
+        if key.startswith("grad_full/"):
+            name = key.split("/", 1)[1]
+            e = _relL2(params[name].grad, g[key])
+            assert e < 2e-2, (name, e)        # relative L2 over the tensor; shallow layers measure ~1e-4
+
+
+def test_proposal_losses_reach_the_backbone(cuda, gold):
+    """the ScoreNet / NPCS losses must back-propagate through the proposal re-voxelisation
+    (differentiable voxel mean) into the backbone - compared with the reference's own autograd on the same step."""
+    g, cfg = gold
+    net, batch = _model(cuda, cfg)
+    net.zero_grad()
+    out = net.training_step(batch, training_schedule=(0, 0), rand=torch.from_numpy(g["rand"]).to(cuda))
+    (out["loss_prop_score"] + out["loss_prop_npcs"]).backward()
+    params = dict(net.named_parameters())
+    seen = 0
+    for key in g.files:
+        if not key.startswith("grad_prop/"):
+            continue
+        name = key.split("/", 1)[1]
+        ref = g[key]
+        if not np.any(ref):
+            continue
+        grad = params[name].grad
+        assert grad is not None and float(grad.abs().max()) > 0, name
+        e = _relL2(grad, ref)
+        assert e < 2e-2, (name, e)
+        seen += name.startswith("backbone")
+    assert seen >= 3
+    assert float(net.engine.flat_grad.abs().max()) > 0
+
+
+def test_segmented_voxelize_stage_is_bit_exact(cuda, gold):
+    """grouping_utils.py:47-104 in isolation on the reference's own stage inputs: voxel coordinates and the
+    point -> voxel map are integer outputs => bit-exact; voxel features (means of backbone features) 1e-5."""
+    from gapartnet_b200.network.grouping_utils import segmented_voxelize
+
+    g, cfg = gold
+    xyz = torch.from_numpy(g["prop_pt_xyz"]).to(cuda)
+    off = torch.from_numpy(g["proposal_offsets"]).to(cuda)
+    pidx = torch.from_numpy(g["proposal_indices"]).to(cuda)
+    n_per = (off[1:] - off[:-1]).long()
+    feats = torch.arange(xyz.shape[0] * 16, device=cuda, dtype=torch.float32).view(-1, 16) % 97
+    vf, vc, pcid = segmented_voxelize(xyz, feats, off, pidx, n_per, 28, 50, rand=torch.from_numpy(g["rand"]).to(cuda))
+    np.testing.assert_array_equal(vc.cpu().numpy(), g["voxel_coords"])
+    np.testing.assert_array_equal(pcid.cpu().numpy(), g["pc_voxel_id"])

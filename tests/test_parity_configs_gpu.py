@@ -1,0 +1,225 @@
+"""GPU parity at the sizes BASELINE.json names, against the CPU oracle evaluated in fp64 (task 1).
+
+  cfg2  SubMConv3d 3^3 16->16 single layer, 20 k points x 8 scenes, voxel 0.02: forward / dgrad / wgrad
+  cfg3  the benchmarked step itself: 16 x 20 000 points, 7-level U-Net, CUDA-graph replay with the side-stream overlaps
+        on, voxelize + 13 rulebooks inside the graph - level-0 coordinates, point->voxel map and ALL 13 pair tables
+        bit-exact, per-point logits <= 1e-3 relative, per-level gradient bars
+  cfg5  dense-scene stress: 200 k points x 4 scenes, voxel 0.01, 256^3 grid: bit-exact voxelisation and rulebooks at
+        levels 0/1, a 2-level network forward/backward against the fp64 oracle at that size
+
+The oracle (oracle/spconv_cpu.py, numpy rulebooks, numpy voxelize) is test infrastructure: the product never imports it.
+Row order: the engine emits voxels in lexicographic (batch,x,y,z) order, the same canonical order the oracle's
+np.unique produces, so tables are compared entry by entry (stronger than comparing pair sets)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from gapartnet_b200 import ops, synthetic
+from gapartnet_b200.engine import SparseUNetEngine
+from gapartnet_b200.network import backbone as mirror
+from oracle import rulebook as rb
+from oracle import spconv_cpu as osp
+from oracle import voxelize as ovox
+
+from util import collate_np, rel_err
+
+pytestmark = pytest.mark.gpu
+CH7 = [16, 32, 48, 64, 80, 96, 112]
+
+
+def _oracle_inputs(scs, voxel, min_shape):
+    scenes = []
+    for sc in scs:
+        vf, vc, pcid, rng = ovox.apply_voxelization(sc.points, [voxel] * 3, min_shape=min_shape)
+        scenes.append(dict(vf=vf, vc=vc, pcid=pcid, shape=rng))
+    return collate_np(scenes)
+
+
+def _relL2(a, b):
+    a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cfg2_single_subm_layer_b8(cuda):
+    """BASELINE.json configs[1]: one SubMConv3d(16->16, k3) forward / input gradient / weight gradient on the level-0
+    rows of 8 scenes x 20 000 points at voxel 0.02 (~59 k rows, ~670 k pairs), tcgen05 3xTF32 path vs fp64."""
+    B, n, voxel, S = 8, 20000, 0.02, 128
+    scs = [synthetic.planes(2000 + b, n) for b in range(B)]
+    feats, idx, shape, _ = _oracle_inputs(scs, voxel, S)
+    M = idx.shape[0]
+    assert 40000 < M < 90000
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(M, 16, generator=g, dtype=torch.float64)
+    w = torch.randn(16, 27, 16, generator=g, dtype=torch.float64) * 0.1      # KRSC [Cout, K, Cin]
+    dy = torch.randn(M, 16, generator=g, dtype=torch.float64)
+    tbl = rb.subm3_table(idx, shape)
+    xo = x.clone().requires_grad_(True)
+    wo = w.clone().requires_grad_(True)
+    yo = osp._apply_table(xo, wo.permute(1, 2, 0), tbl, M)
+    yo.backward(dy)
+
+    ti = torch.from_numpy(idx).to(cuda)
+    grid = ops.grid_from_coords(ti, B, shape)
+    book = ops.rulebook_subm3(ti, M, grid)
+    np.testing.assert_array_equal(book.nbr.cpu().numpy(), tbl)               # indice pairs: bit-exact
+    xg, wg, dyg = x.float().to(cuda), w.float().to(cuda).contiguous(), dy.float().to(cuda)
+    y = ops.conv_fwd(xg, wg, book.nbr, 27, M, use_tc=True)
+    dx = ops.conv_fwd(dyg, wg, book.nbr, 27, M, transpose=True, flip=True, use_tc=True)
+    dw = torch.zeros_like(wg)
+    ops.conv_wgrad(xg, dyg, dw, book.nbr, 27, M, use_tc=True)
+    # 3xTF32 carries ~2^-21 per product; K = 432: measured ~3e-6 of the largest output
+    assert rel_err(y, yo) < 5e-5
+    assert rel_err(dx, xo.grad) < 5e-5
+    assert rel_err(dw, wo.grad) < 5e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cfg3_benchmarked_step_against_fp64_oracle(cuda):
+    """BASELINE.json configs[2] exactly as bench.py runs it (same scenes, same weights seed, CUDA graph, overlaps)."""
+    import gapartnet_b200.spconv.pytorch as sp
+
+    B, n, voxel, S = 16, 20000, 0.02, 128
+    scs = [synthetic.planes(3000 + b, n) for b in range(B)]
+    torch.manual_seed(23333)
+    o_net = mirror.build_sparse_unet(osp, 6, CH7, 2)
+    g_net = mirror.build_sparse_unet(sp, 6, CH7, 2).to(cuda)
+    g_net.load_state_dict(o_net.state_dict())
+    o64 = copy.deepcopy(o_net).double()
+    head = torch.randn(10, 16, generator=torch.Generator().manual_seed(5)) * 0.1
+    labels = torch.from_numpy(np.concatenate([s.sem_labels for s in scs]))
+
+    # ---- oracle, fp64 --------------------------------------------------------------------------------------------
+    torch.set_num_threads(min(torch.get_num_threads(), 16))
+    feats, idx, shape, pcid = _oracle_inputs(scs, voxel, S)
+    assert shape == [S, S, S]
+    x = osp.SparseConvTensor(torch.from_numpy(feats).double(), torch.from_numpy(idx), shape, B)
+    feat_o = o64(x).features[torch.from_numpy(pcid)]
+    logits_o = feat_o @ head.double().t()
+    loss_o = torch.nn.functional.cross_entropy(logits_o, labels)
+    loss_o.backward()
+
+    # ---- engine: the bench step ----------------------------------------------------------------------------------
+    N = B * n
+    eng = SparseUNetEngine(g_net, batch=B, max_points=N, spatial_shape=(S, S, S), voxel_size=voxel, in_channels=6)
+    pts = torch.from_numpy(np.concatenate([s.points for s in scs])).to(cuda)
+    off = torch.arange(B + 1, dtype=torch.int64, device=cuda) * n
+    eng.load_points(pts, off)
+    head_g, lab_g = head.to(cuda), labels.to(cuda)
+    logits_buf = torch.empty(N, 10, device=cuda)
+
+    def step():
+        eng.flat_grad.zero_()
+        eng.build_levels(overlap=True)
+        f = eng.run_forward()
+        logits = f @ head_g.t()
+        logits_buf.copy_(logits)
+        d = torch.softmax(logits, 1)
+        d.scatter_add_(1, lab_g[:, None], torch.full((N, 1), -1.0, device=cuda))
+        torch.mm(d * (1.0 / N), head_g, out=eng.d_pc_feature)
+        eng.run_backward()
+
+    momentum = eng.momentum
+    eng.momentum = 0.0
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    counts = eng.calibrate()
+    eng.momentum = momentum
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    graph.replay()
+    torch.cuda.synchronize()
+
+    # ---- integer outputs: bit-exact -------------------------------------------------------------------------------
+    assert counts[0] == idx.shape[0]
+    np.testing.assert_array_equal(eng.coords[0][:counts[0]].cpu().numpy(), idx)
+    np.testing.assert_array_equal(eng.pc_voxel_id.cpu().numpy(), pcid)
+    cur = x
+    lvl_idx, lvl_shape = idx, shape
+    for L in range(len(CH7)):
+        tbl = cur.indice_dict[("subm", f"subm{L + 1}")]
+        assert counts[L] == tbl.shape[1], (L, counts[L], tbl.shape)
+        np.testing.assert_array_equal(eng.nbr[L][:, :counts[L]].cpu().numpy(), tbl)
+        if L + 1 < len(CH7):
+            _, _, child, parent8 = cur.indice_dict[("spconv", f"spconv{L + 1}")]
+            np.testing.assert_array_equal(eng.child[L][:, :counts[L + 1]].cpu().numpy(), child)
+            np.testing.assert_array_equal(eng.parent8[L][:, :counts[L]].cpu().numpy(), parent8)
+            out_c, _, _, _ = rb.down2_tables(lvl_idx, lvl_shape)
+            np.testing.assert_array_equal(eng.coords[L + 1][:counts[L + 1]].cpu().numpy(), out_c)
+            lvl_idx, lvl_shape = out_c, [s_ // 2 for s_ in lvl_shape]
+
+    # ---- floating point: north_star tolerance 1e-3 relative on the logits (measured ~2e-5) ------------------------
+    assert rel_err(eng.pc_feature, feat_o) < 1e-3
+    assert rel_err(logits_buf, logits_o) < 1e-3
+    per_point = (logits_buf.double().cpu() - logits_o).abs().max(1).values / logits_o.abs().max()
+    assert float(per_point.max()) < 1e-3
+
+    # ---- gradients per U-Net level (relative L2 over all parameters of the level, vs fp64).  The deepest levels
+    # hold 58 / 233 rows for 16 scenes: BatchNorm backward over so few rows amplifies fp32 rounding (any fp32
+    # implementation, incl. the CPU oracle in fp32, shows it), hence the graded bars. -----------------------------------
+    bars = [2e-3, 2e-3, 2e-3, 5e-3, 1e-2, 3e-2, 5e-2]
+    num = [0.0] * len(CH7)
+    den = [0.0] * len(CH7)
+    for (name, p64), pg in zip(o64.named_parameters(), g_net.parameters()):
+        L = name.count("ublock") - 1 if "ublock" in name else 0
+        num[L] += float((pg.grad.double().cpu() - p64.grad).square().sum())
+        den[L] += float(p64.grad.square().sum())
+    errs = [(a / b) ** 0.5 for a, b in zip(num, den)]
+    for L, (e, bar) in enumerate(zip(errs, bars)):
+        assert e < bar, (L, errs)
+    assert (sum(num) / sum(den)) ** 0.5 < 5e-3, errs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cfg5_dense_scenes_b4(cuda):
+    """BASELINE.json configs[4]: 200 000 points per scene, voxel 0.01, batch 4 (~930 k level-0 rows, 3.3 M pairs)."""
+    import gapartnet_b200.spconv.pytorch as sp
+
+    B, n, voxel, S = 4, 200000, 0.01, 256
+    scs = [synthetic.planes(5000 + b, n) for b in range(B)]
+    feats, idx, shape, pcid = _oracle_inputs(scs, voxel, S)
+    assert shape == [S, S, S]
+    torch.manual_seed(9)
+    chans = [16, 32]
+    o_net = mirror.build_sparse_unet(osp, 6, chans, 1).double()
+    g_net = mirror.build_sparse_unet(sp, 6, chans, 1).to(cuda)
+    g_net.load_state_dict({k: v.float() for k, v in o_net.state_dict().items()})
+    torch.set_num_threads(min(torch.get_num_threads(), 16))
+    x = osp.SparseConvTensor(torch.from_numpy(feats).double(), torch.from_numpy(idx), shape, B)
+    feat_o = o_net(x).features[torch.from_numpy(pcid)]
+    w = torch.randn(16, 4, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    (feat_o @ w).square().mean().backward()
+
+    N = B * n
+    eng = SparseUNetEngine(g_net, batch=B, max_points=N, spatial_shape=(S, S, S), voxel_size=voxel, in_channels=6)
+    pts = torch.from_numpy(np.concatenate([s.points for s in scs])).to(cuda)
+    eng.load_points(pts, torch.arange(B + 1, dtype=torch.int64, device=cuda) * n)
+    eng.build_levels()
+    counts = eng.calibrate()
+    assert counts[0] == idx.shape[0] and counts[0] > 800000
+    np.testing.assert_array_equal(eng.coords[0][:counts[0]].cpu().numpy(), idx)
+    np.testing.assert_array_equal(eng.pc_voxel_id.cpu().numpy(), pcid)
+    np.testing.assert_array_equal(eng.nbr[0][:, :counts[0]].cpu().numpy(), x.indice_dict[("subm", "subm1")])
+    _, _, child, parent8 = x.indice_dict[("spconv", "spconv1")]
+    np.testing.assert_array_equal(eng.child[0][:, :counts[1]].cpu().numpy(), child)
+    np.testing.assert_array_equal(eng.parent8[0][:, :counts[0]].cpu().numpy(), parent8)
+    np.testing.assert_array_equal(eng.nbr[1][:, :counts[1]].cpu().numpy(), x.indice_dict[("subm", "subm2")])
+
+    eng.zero_grad()
+    f = eng.run_forward()
+    assert rel_err(f, feat_o) < 1e-3
+    fl = f.detach().clone().requires_grad_(True)
+    (fl @ w.float().to(cuda)).square().mean().backward()
+    eng.d_pc_feature.copy_(fl.grad)
+    eng.run_backward()
+    torch.cuda.synchronize()
+    for (name, p64), pg in zip(o_net.named_parameters(), g_net.parameters()):
+        assert _relL2(pg.grad, p64.grad) < 2e-3, name

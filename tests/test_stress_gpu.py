@@ -62,7 +62,7 @@ def test_dense_scene_stress_properties(cuda):
     # forward / backward: finite, non-trivial, repeatable.  The forward is repeatable to fp32 rounding (measured 8e-7).
     # The gradients carry the order noise of the fp32 reductions of the split-K convs, amplified by BatchNorm
     # backward over the ~30 rows of the deepest level of this 2-scene batch (measured 0.7e-3 .. 2.5e-3 of the largest
-    # gradient, with or without the stream overlaps; tests/debug_repeat.py) - the bound only catches gross races.
+    # gradient, with or without the stream overlaps; tools/debug_repeat.py) - the bound only catches gross races.
     grads, feats = [], []
     for _ in range(2):
         eng.zero_grad()
@@ -86,7 +86,7 @@ def test_full_size_tensor_core_path_within_tolerance(cuda):
     tolerance: per-point logits within 1e-3 relative (here: of the largest logit; measured 1.2e-5).  Gradients are
     compared at 5e-3 of the largest gradient: measured 1.0e-3, all of it at the two deepest levels (58 / 233 rows) whose
     BatchNorm backward over a handful of rows amplifies fp32 noise ~1000x - two runs of the SAME tensor-core path already
-    differ by 5.6e-5 there because of the order of the fp32 atomics (tests/debug_grad_tol.py prints the per-layer
+    differ by 5.6e-5 there because of the order of the fp32 atomics (tools/debug_grad_tol.py prints the per-layer
     breakdown); the small-scale engine tests pin the gradients against the fp64 oracle."""
     import copy
 

@@ -37,3 +37,27 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     b = b.detach().double().cpu()
     denom = b.abs().max().item()
     return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+def deterministic_weights(module, seed: int = 0, gains=None):
+    """Fill every parameter from numpy streams keyed by the parameter NAME (independent of torch's RNG and of module
+    construction order), so that tests/golden/ref_harness.py (the reference's modules) and the GPU tests (this repo's
+    modules, same state_dict keys) hold bit-identical weights without shipping them in a fixture.
+    gains: {name prefix: factor} applied to matrices whose name starts with the prefix."""
+    import zlib
+
+    gains = gains or {}
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            g = np.random.default_rng([seed, zlib.crc32(name.encode())])
+            if p.dim() >= 2:
+                fan_in = int(np.prod(p.shape[1:]))
+                w = g.normal(0.0, 1.0 / np.sqrt(fan_in), size=tuple(p.shape))
+                for pre, f in gains.items():
+                    if name.startswith(pre):
+                        w = w * f
+            elif name.endswith("weight"):
+                w = 1.0 + 0.1 * g.normal(size=tuple(p.shape))
+            else:
+                w = 0.1 * g.normal(size=tuple(p.shape))
+            p.copy_(torch.from_numpy(w.astype(np.float32)).to(p.device))
