@@ -268,6 +268,32 @@ __global__ void k_vox_mean(float* __restrict__ vfeat, const int* __restrict__ vc
     vfeat[t] = vfeat[t] / (float)vcnt[row];
 }
 
+// points of [batch_offsets[0], batch_offsets[B]) the voxeliser dropped (pc_voxel_id < 0): *d_count += their number
+__global__ void k_count_dropped(const int* __restrict__ pc_voxel_id, const long long* __restrict__ batch_offsets, int B,
+                                int N, int* __restrict__ d_count) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
+    const long long lo = batch_offsets[0], hi = batch_offsets[B];
+    int c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+        c += (i >= lo && i < hi && pc_voxel_id[i] < 0) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(d_count, c);
+}
+
+extern "C" int gp_count_dropped(const int* pc_voxel_id, const int64_t* batch_offsets, int batch, int N, int* d_count,
+                                void* stream_) {
+    GP_CHECK_ARG(batch > 0 && N >= 0, "gp_count_dropped: bad sizes");
+    if (N == 0) return GP_OK;
+    int blocks = gp_cdiv(N, 256 * 8);
+    GP_CUDA(gp_launch(k_count_dropped, dim3(blocks), dim3(256), 0, (cudaStream_t)stream_, pc_voxel_id,
+                      (const long long*)batch_offsets, batch, N, d_count));
+    gp_note_launch(1);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
 extern "C" int gp_scene_range(const float* xyz, int xyz_stride, const int64_t* batch_offsets,
                               int batch, float pad, float* range_min, float* range_max,
                               void* stream_) {

@@ -54,7 +54,7 @@ class SparseUNetEngine:
 
     def __init__(self, net: nn.Module, batch: int, max_points: int, spatial_shape: Sequence[int],
                  voxel_size: float, in_channels: int, max_rows: Optional[Sequence[int]] = None,
-                 input_needs_grad: bool = False, bn_eps: float = 1e-4, bn_momentum: float = 0.1,
+                 input_needs_grad: bool = False, bn_eps: Optional[float] = None, bn_momentum: Optional[float] = None,
                  use_tc: Optional[bool] = None):
         p0 = next(net.parameters())
         if not p0.is_cuda:
@@ -65,7 +65,10 @@ class SparseUNetEngine:
         self.shape0 = tuple(int(s) for s in spatial_shape)
         self.voxel_size = float(voxel_size)
         self.in_channels = in_channels
-        self.eps, self.momentum = float(bn_eps), float(bn_momentum)
+        # None = every BatchNorm1d module's own eps / momentum (norm_fn of network/model.py:86 sets 1e-4 / 0.1);
+        # a number overrides all layers (tests freeze the running statistics with momentum 0 during warm-up)
+        self.eps = None if bn_eps is None else float(bn_eps)
+        self.momentum = None if bn_momentum is None else float(bn_momentum)
         self.training = True
         self.input_needs_grad = input_needs_grad
         self._stream = None
@@ -115,6 +118,12 @@ class SparseUNetEngine:
         # static inputs
         self.points = f32(self.N, in_channels)
         self.batch_offsets = torch.zeros(self.B + 1, dtype=torch.int64, device=dev)
+        self.n_loaded = self.N
+        # points the voxeliser had to drop because they fall outside the static grid (sticky device counter, summed over
+        # build_levels() calls; the reference grows the grid instead and asserts pc_voxel_id >= 0,
+        # dataset/gapartnet.py:196-198) - read by check_dropped() / calibrate() / level_counts()
+        self.d_dropped = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.fwd_generation = 0
 
         # ---- program ----------------------------------------------------------------------------
         self._fwd: List[Callable[[], None]] = []
@@ -161,6 +170,14 @@ class SparseUNetEngine:
 
     def _s(self):
         return self._cur_stream
+
+    def _bn_eps(self, bn: nn.BatchNorm1d) -> float:
+        return float(bn.eps) if self.eps is None else self.eps
+
+    def _bn_momentum(self, bn: nn.BatchNorm1d) -> float:
+        if self.momentum is not None:
+            return self.momentum
+        return 0.1 if bn.momentum is None else float(bn.momentum)
 
     def _add_pack(self, w: torch.Tensor, w_sk: int, w_sci: int, w_sco: int, flip: int, K: int, cin: int,
                   cout: int, cin_real: int = 0) -> torch.Tensor:
@@ -282,9 +299,9 @@ class SparseUNetEngine:
             if train and split and not C.gp_bn_cluster_ok(n_out, hint):
                 C.gp_col_stats(y.ptr, y.ld, Cout, _p(d_n_out), n_out, _p(stats), s)
                 st = _p(stats)
-            C.gp_bn_fwd_fused(y.ptr, y.ld, Cout, _p(d_n_out), n_out, st, g_ptr, b_ptr, eng.eps, eng.momentum,
-                              rm_ptr, rv_ptr, 0 if train else 1, res_ptr, res_ld, int(relu), a.ptr, a.ld,
-                              vec_ptr, hint, s)
+            C.gp_bn_fwd_fused(y.ptr, y.ld, Cout, _p(d_n_out), n_out, st, g_ptr, b_ptr, eng._bn_eps(bn),
+                              eng._bn_momentum(bn), rm_ptr, rv_ptr, 0 if train else 1, res_ptr, res_ld, int(relu),
+                              a.ptr, a.ld, vec_ptr, hint, s)
 
         self._fwd.append(fwd)
         self._n_launch_fwd += 3
@@ -377,8 +394,8 @@ class SparseUNetEngine:
             if eng.training and not C.gp_bn_cluster_ok(n, hint):
                 C.gp_col_stats(x.ptr, x.ld, Cc, _p(d_n), n, _p(stats), s)
                 st = _p(stats)
-            C.gp_bn_fwd_fused(x.ptr, x.ld, Cc, _p(d_n), n, st, g_ptr, b_ptr, eng.eps, eng.momentum, rm_ptr, rv_ptr,
-                              0 if eng.training else 1, None, 0, int(relu), a.ptr, a.ld, vec_ptr, hint, s)
+            C.gp_bn_fwd_fused(x.ptr, x.ld, Cc, _p(d_n), n, st, g_ptr, b_ptr, eng._bn_eps(bn), eng._bn_momentum(bn),
+                              rm_ptr, rv_ptr, 0 if eng.training else 1, None, 0, int(relu), a.ptr, a.ld, vec_ptr, hint, s)
 
         self._fwd.append(fwd)
         self._n_launch_fwd += 3
@@ -479,10 +496,12 @@ class SparseUNetEngine:
         params = list(net.parameters())
         total = sum(p.numel() for p in params)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self._grad_views = []
         off = 0
         for p in params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            self._grad_views.append((p, self.flat_grad[off:off + p.numel()].view_as(p)))
             off += p.numel()
+        self.bind_grads()
         x0 = _Act(self.vox_feats, 0)
         x0.needs_grad = self.input_needs_grad
         stem = list(net.stem._modules.values()) if net.stem is not None else []
@@ -549,6 +568,7 @@ class SparseUNetEngine:
                       _p(self.rmax), 1, *g0.shape, _p(g0.words), _p(g0.prefix), _p(self.scan_tmp[0]),
                       _p(self.pt_cell), self.max_rows[0], _p(self.vox_feats), _p(self.vox_cnt),
                       _p(self.coords[0]), _p(self.pc_voxel_id), _p(self.d_n[0]), _p(self.batch_splits), s)
+        C.gp_count_dropped(_p(self.pc_voxel_id), _p(self.batch_offsets), B, N, _p(self.d_dropped), s)
         if not overlap:
             self._lvl_events = None
             self._rulebooks(s, range(self.depth))
@@ -606,6 +626,7 @@ class SparseUNetEngine:
         else:
             self.pack_weights()
         s = self._bind_stream()
+        self.fwd_generation += 1
         if self._stat_used:
             C.gp_memset(_p(self._stat_arena), 0, self._stat_used * 8, s)
         for op in self._fwd:
@@ -616,8 +637,26 @@ class SparseUNetEngine:
                          self.pc_feature.stride(0), s)
         return self.pc_feature
 
+    def bind_grads(self) -> int:
+        """(re-)attach every parameter's .grad to its view of the flat gradient arena.  The kernels write raw arena
+        pointers captured at build time, so a `.grad = None` left behind by `optimizer.zero_grad()` / `net.zero_grad()`
+        (set_to_none=True is torch's default) would make the optimizer silently skip the backbone: run_backward()
+        calls this first.  -> number of parameters that had to be re-bound (a re-bound arena slice is zeroed, which is
+        what zero_grad meant)."""
+        n = 0
+        for p, view in self._grad_views:
+            g = p.grad
+            if g is None or g.data_ptr() != view.data_ptr() or g.shape != view.shape:
+                view.zero_()
+                p.grad = view
+                n += 1
+        return n
+
     def run_backward(self):
-        """consumes self.d_pc_feature [N, C0]; accumulates into every parameter's .grad."""
+        """consumes self.d_pc_feature [N, C0]; accumulates into every parameter's .grad (= views of self.flat_grad;
+        call zero_grad() - or optimizer.zero_grad(), either flavour - between steps)."""
+        if not torch.cuda.is_current_stream_capturing():
+            self.bind_grads()
         s = self._bind_stream()
         if self.overlap_wgrad:
             if self._side_obj is None:
@@ -638,9 +677,18 @@ class SparseUNetEngine:
 
     # convenience --------------------------------------------------------------------------------
     def load_points(self, points: torch.Tensor, batch_offsets: torch.Tensor):
-        assert points.shape == self.points.shape, (points.shape, self.points.shape)
-        self.points.copy_(points, non_blocking=True)
-        self.batch_offsets.copy_(batch_offsets, non_blocking=True)
+        """points [n, C] with n <= max_points, batch_offsets [b+1] with b <= batch (the reference's val/test loaders
+        use drop_last=False: a last partial batch, or scenes with fewer points, are legal).  Rows beyond
+        batch_offsets[-1] are ignored by the voxeliser; missing scenes are empty segments."""
+        n, b1 = points.shape[0], batch_offsets.numel()
+        if points.shape[1] != self.in_channels or n > self.N or b1 > self.B + 1 or b1 < 2:
+            raise GapartError(f"load_points: got {tuple(points.shape)} points / {b1 - 1} scenes, engine holds "
+                              f"<= {self.N} x {self.in_channels} / {self.B}")
+        self.points[:n].copy_(points, non_blocking=True)
+        self.batch_offsets[:b1].copy_(batch_offsets, non_blocking=True)
+        if b1 < self.B + 1:
+            self.batch_offsets[b1:] = self.batch_offsets[b1 - 1]
+        self.n_loaded = n
 
     def forward_points(self, points: torch.Tensor, batch_offsets: torch.Tensor) -> torch.Tensor:
         self.load_points(points, batch_offsets)
@@ -648,12 +696,26 @@ class SparseUNetEngine:
         return self.run_forward()
 
     def zero_grad(self):
+        self.bind_grads()
         self.flat_grad.zero_()
+
+    def check_dropped(self) -> int:
+        """host sync: raise if any point fell outside the static voxel grid since the last check (such a point would get
+        zero features and no gradient).  Size `spatial_shape` from the data range / voxel size - the reference's own
+        voxel size is 0.01, i.e. a unit-ball scene needs a 256^3 grid, 0.02 fits 128^3."""
+        n = int(self.d_dropped.item())
+        if n:
+            self.d_dropped.zero_()
+            raise GapartError(f"{n} point(s) fell outside the {self.shape0} voxel grid at voxel size {self.voxel_size} "
+                              "(the reference grows the grid and asserts pc_voxel_id >= 0, dataset/gapartnet.py:196-198): "
+                              "build the engine with a larger spatial_shape")
+        return 0
 
     def calibrate(self) -> List[int]:
         """one host sync: remember the current per-level row counts as launch hints (+25% head-room).
         Call after a representative build_levels(); plans captured in CUDA graphs afterwards use them."""
         counts = self.level_counts()
+        self.check_dropped()
         self.rows_hint[:] = [int(c * 1.25) + 1 for c in counts]
         return counts
 

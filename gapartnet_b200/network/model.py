@@ -96,12 +96,22 @@ class _EngineBackbone(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, batch_offsets, engine: SparseUNetEngine, anchor):
         ctx.engine = engine
-        return engine.forward_points(points, batch_offsets).clone()
+        out = engine.forward_points(points, batch_offsets)[:points.shape[0]].clone()
+        ctx.generation = engine.fwd_generation
+        return out
 
     @staticmethod
     def backward(ctx, grad):
         eng = ctx.engine
-        eng.d_pc_feature.copy_(grad)
+        if ctx.generation != eng.fwd_generation:
+            # the engine keeps ONE set of activations / rulebooks: a second forward (gradient accumulation, a
+            # validation batch inside the step) overwrote what this backward needs
+            raise RuntimeError("SparseUNetEngine ran another forward before this backward: its activations are gone "
+                               "(run backward first, or use one engine per in-flight batch)")
+        n = grad.shape[0]
+        if n < eng.N:
+            eng.d_pc_feature[n:].zero_()
+        eng.d_pc_feature[:n].copy_(grad)
         eng.run_backward()
         return None, None, None, torch.zeros((), device=grad.device)
 

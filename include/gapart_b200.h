@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GP_ABI_VERSION 1
+#define GP_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------- */
 int gp_version(void);
@@ -74,6 +74,13 @@ int gp_voxelize(const float* xyz, int xyz_stride, const float* feats, int C, int
                 int Z, uint32_t* words, int* prefix, int* scan_tmp, uint32_t* pt_cell,
                 int max_voxels, float* voxel_feats, int* voxel_cnt, int* voxel_coords4,
                 int* pc_voxel_id, int* d_num_voxels, int* d_batch_splits, void* stream);
+
+/* The reference asserts that voxelisation drops nothing (`assert (pc_voxel_id >= 0).all()`,
+ * gapartnet/dataset/gapartnet.py:196; pdb trap at gapartnet/network/model.py:328-330) and grows the grid to fit the
+ * data (:198).  A sync-free engine works on a static grid instead, so the check is a device-side sticky counter:
+ * *d_count += number of points i in [batch_offsets[0], batch_offsets[batch]) with pc_voxel_id[i] < 0. */
+int gp_count_dropped(const int* pc_voxel_id, const int64_t* batch_offsets, int batch, int N, int* d_count,
+                     void* stream);
 
 /* ---- rulebooks (indice pairs) ---------------------------------------------------------------- */
 /* SubMConv3d(kernel_size=3, padding=1, indice_key=...) pair table
