@@ -36,12 +36,17 @@ __global__ void k_pack_xyzl(const float* __restrict__ xyz, int stride, const int
 // float4 (x,y,z,label) stream of that scene is a broadcast load per warp.  MODE 0 writes the neighbour
 // table, MODE 1 unions on the fly (fused clustering).
 __device__ __forceinline__ int uf_find(int* parent, int i) {
-    // volatile: other threads re-link roots concurrently, a stale read only costs another hop
+    // volatile: other threads re-link roots concurrently, a stale read only costs another hop.  Path halving: a node
+    // is re-pointed at its grandparent on the way up.  Links are only ever created at roots and always towards the
+    // smaller index, so an ancestor stays an ancestor and the plain (racy) store can only shorten a chain - without it
+    // the "one class everywhere" components of an untrained network (15 k points each) made every find walk long chains
     volatile int* vp = parent;
     int p = vp[i];
     while (p != i) {
+        const int gp = vp[p];
+        if (gp != p) vp[i] = gp;
         i = p;
-        p = vp[i];
+        p = gp;
     }
     return i;
 }
@@ -261,8 +266,11 @@ __global__ void __launch_bounds__(128) k_cg_cluster(const float4* __restrict__ p
                                                     int use_labels, const unsigned* __restrict__ mn, float inv_cell,
                                                     const int* __restrict__ starts, const int* __restrict__ order,
                                                     int* __restrict__ num, int* __restrict__ parent) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q) return;
+    // queries in cell order: the lanes of a warp sit in the same or adjacent cells and walk (nearly) the same candidate
+    // ranges - broadcast loads instead of 32 scattered ones
+    const int q = order[t];
     const float4 c = pts[q];
     const int b = batch_indices[q];
     const int lab = __float_as_int(c.w);

@@ -55,13 +55,25 @@ class SparseUNetEngine:
     def __init__(self, net: nn.Module, batch: int, max_points: int, spatial_shape: Sequence[int],
                  voxel_size: float, in_channels: int, max_rows: Optional[Sequence[int]] = None,
                  input_needs_grad: bool = False, bn_eps: Optional[float] = None, bn_momentum: Optional[float] = None,
-                 use_tc: Optional[bool] = None):
+                 use_tc: Optional[bool] = None, source: str = "points",
+                 levels_from: Optional["SparseUNetEngine"] = None):
+        """source = "points": level 0 comes from voxelising `self.points` (load_points -> build_levels).
+        source = "sparse": level 0 is a caller-provided SparseConvTensor (features [M, C] + indices [M, 4] (b,x,y,z) in
+        ANY row order, the spconv.SparseConvTensor contract of structure/point_cloud.py:158-162 and model.py:323-327):
+        load_sparse -> build_levels; run_forward returns per-VOXEL features in the caller's row order and
+        run_backward consumes a per-voxel gradient (and yields the input-feature gradient if input_needs_grad).
+        levels_from = another engine on the SAME coordinates (GAPartNet's score and NPCS U-Nets both run on the
+        re-voxelised proposals, model.py:358,392): coordinates, occupancy directories and all rulebooks are shared,
+        only build them once on the owner."""
         p0 = next(net.parameters())
         if not p0.is_cuda:
             raise GapartError("SparseUNetEngine needs the module on a CUDA device")
         self.dev = p0.device
         self.net = net
         self.B, self.N = int(batch), int(max_points)
+        # scenes that can be non-empty this step (<= batch): a host-side hint that bounds the occupancy-directory
+        # passes of sparse-in engines with a large static batch (proposal grids); None = batch
+        self.active_batch: Optional[int] = None
         self.shape0 = tuple(int(s) for s in spatial_shape)
         self.voxel_size = float(voxel_size)
         self.in_channels = in_channels
@@ -72,6 +84,10 @@ class SparseUNetEngine:
         self.training = True
         self.input_needs_grad = input_needs_grad
         self._stream = None
+        if source not in ("points", "sparse"):
+            raise ValueError(source)
+        self.source = source
+        self.levels_owner = levels_from
 
         # ---- level geometry ---------------------------------------------------------------
         chans = list(net.ublock.channels)
@@ -99,25 +115,43 @@ class SparseUNetEngine:
         i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         # ---- level state --------------------------------------------------------------------
-        self.coords = [i32(m, 4) for m in self.max_rows]
-        self.d_n = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in self.max_rows]
-        self.grids = [ops.GridDir.alloc(self.B, s, dev) for s in self.shapes]
-        self.scan_tmp = [g.scan_tmp() for g in self.grids]
-        self.nbr = [i32(27, m) for m in self.max_rows]
-        self.child = [i32(8, self.max_rows[L + 1]) for L in range(depth - 1)]
-        self.parent8 = [i32(8, self.max_rows[L]) for L in range(depth - 1)]
-        # voxelize workspaces
-        self.vox_feats = f32(self.max_rows[0], in_channels)
-        self.vox_cnt = i32(self.max_rows[0])
-        self.pt_cell = i32(self.N)
-        self.pc_voxel_id = i32(self.N)
-        self.batch_splits = i32(self.B + 1)
-        self.rmin = f32(self.B, 3)
-        self.rmax = f32(self.B, 3)
-        self.vs = torch.full((3,), self.voxel_size, dtype=torch.float32, device=dev)
-        # static inputs
-        self.points = f32(self.N, in_channels)
-        self.batch_offsets = torch.zeros(self.B + 1, dtype=torch.int64, device=dev)
+        if levels_from is not None:
+            o = levels_from
+            if (o.B, o.shapes, o.max_rows, o.in_channels) != (self.B, self.shapes, self.max_rows, in_channels):
+                raise GapartError("levels_from: the two engines must agree on batch, shapes, row bounds and channels")
+            self.coords, self.d_n, self.grids, self.scan_tmp = o.coords, o.d_n, o.grids, o.scan_tmp
+            self.nbr, self.child, self.parent8 = o.nbr, o.child, o.parent8
+            self.vox_feats, self.vox_cnt, self.pt_cell, self.pc_voxel_id = o.vox_feats, o.vox_cnt, o.pt_cell, o.pc_voxel_id
+            self.batch_splits, self.rmin, self.rmax, self.vs = o.batch_splits, o.rmin, o.rmax, o.vs
+            self.points, self.batch_offsets = o.points, o.batch_offsets
+            self.row_of_rank, self.d_err = o.row_of_rank, o.d_err
+        else:
+            self.coords = [i32(m, 4) for m in self.max_rows]
+            self.d_n = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in self.max_rows]
+            self.grids = [ops.GridDir.alloc(self.B, s, dev) for s in self.shapes]
+            self.scan_tmp = [g.scan_tmp() for g in self.grids]
+            self.nbr = [i32(27, m) for m in self.max_rows]
+            self.child = [i32(8, self.max_rows[L + 1]) for L in range(depth - 1)]
+            self.parent8 = [i32(8, self.max_rows[L]) for L in range(depth - 1)]
+            # voxelize workspaces
+            self.vox_feats = f32(self.max_rows[0], in_channels)
+            pts_mode = source == "points"
+            self.vox_cnt = i32(self.max_rows[0] if pts_mode else 1)
+            self.pt_cell = i32(self.N if pts_mode else 1)
+            self.pc_voxel_id = i32(self.N if pts_mode else 1)
+            self.batch_splits = i32(self.B + 1)
+            self.rmin = f32(self.B if pts_mode else 1, 3)
+            self.rmax = f32(self.B if pts_mode else 1, 3)
+            self.vs = torch.full((3,), self.voxel_size, dtype=torch.float32, device=dev)
+            # static inputs
+            self.points = f32(self.N if pts_mode else 1, in_channels)
+            self.batch_offsets = torch.zeros(self.B + 1, dtype=torch.int64, device=dev)
+            # sparse-in: caller rows may come in any order -> rank -> row map of the level-0 directory; d_err collects
+            # bit0 = coordinate outside spatial_shape / batch, bit1 = duplicate coordinate (check_indices())
+            self.row_of_rank = i32(self.max_rows[0]) if not pts_mode else None
+            self.d_err = torch.zeros(1, dtype=torch.int32, device=dev)
+            if not pts_mode:
+                self.grids[0].row_of_rank = self.row_of_rank
         self.n_loaded = self.N
         # points the voxeliser had to drop because they fall outside the static grid (sticky device counter, summed over
         # build_levels() calls; the reference grows the grid instead and asserts pc_voxel_id >= 0,
@@ -516,8 +550,9 @@ class SparseUNetEngine:
         self.x0 = x0
         self.out_grad = self._grad_of(out)
         out.grad_ready = True
-        self.pc_feature = torch.empty(self.N, out.C, dtype=torch.float32, device=self.dev)
-        self.d_pc_feature = torch.zeros(self.N, out.C, dtype=torch.float32, device=self.dev)
+        npt = self.N if self.source == "points" else 1
+        self.pc_feature = torch.empty(npt, out.C, dtype=torch.float32, device=self.dev)
+        self.d_pc_feature = torch.zeros(npt, out.C, dtype=torch.float32, device=self.dev)
         if self._packs:
             import numpy as np
             dt = np.dtype([("W", "<u8"), ("out", "<u8"), ("w_sk", "<i8"), ("w_sci", "<i8"), ("w_sco", "<i8"),
@@ -537,6 +572,8 @@ class SparseUNetEngine:
             fn, nl = mk()
             self._bwd.append(fn)
             self._n_launch_bwd += nl
+        # gradient w.r.t. the level-0 input rows [max_rows[0], in_channels]; valid after run_backward()
+        self.in_grad = self.x0.grad if self.input_needs_grad else None
 
     # ------------------------------------------------------------------------------------------
     def build_levels(self, overlap: bool = False):
@@ -549,6 +586,16 @@ class SparseUNetEngine:
         graph); level_counts() / calibrate() join as well."""
         s = self._bind_stream()
         N, B = self.N, self.B
+        if self.levels_owner is not None:
+            return                      # the owner engine built coordinates / directories / rulebooks
+        if self.source == "sparse":
+            g0 = self.grids[0]
+            B = self._batch_now()
+            C.gp_grid_from_coords(_p(self.coords[0]), _p(self.d_n[0]), self.max_rows[0], B, *g0.shape, _p(g0.words),
+                                  _p(g0.prefix), _p(self.scan_tmp[0]), _p(self.row_of_rank), _p(self.d_err), s)
+            self._lvl_events = None
+            self._rulebooks(s, range(self.depth))
+            return
         if overlap:
             if self._side_obj is None:
                 self._side_obj = torch.cuda.Stream(device=self.dev)
@@ -598,15 +645,18 @@ class SparseUNetEngine:
                 self._wait_level(L)
             self._lvl_events = None
 
+    def _batch_now(self) -> int:
+        return self.B if self.active_batch is None else max(1, min(int(self.active_batch), self.B))
+
     def _subm_table(self, L: int, s):
         g = self.grids[L]
-        C.gp_rulebook_subm3(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], self.B, *g.shape,
+        C.gp_rulebook_subm3(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], self._batch_now(), *g.shape,
                             _p(g.words), _p(g.prefix), _p(g.row_of_rank), _p(self.nbr[L]),
                             self.nbr[L].shape[1], s)
 
     def _down_table(self, L: int, s):
         g, g2 = self.grids[L], self.grids[L + 1]
-        C.gp_rulebook_down2(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], self.B, *g.shape,
+        C.gp_rulebook_down2(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], self._batch_now(), *g.shape,
                             _p(g2.words), _p(g2.prefix), _p(self.scan_tmp[L + 1]),
                             self.max_rows[L + 1], _p(self.coords[L + 1]), _p(self.d_n[L + 1]),
                             _p(self.child[L]), self.child[L].shape[1], _p(self.parent8[L]),
@@ -633,6 +683,8 @@ class SparseUNetEngine:
             op()
         self._join_levels()
         o = self.out_act
+        if self.source == "sparse":
+            return o.t                  # per-voxel features [max_rows[0], C0]; rows >= the device count are undefined
         C.gp_gather_rows(o.ptr, o.ld, o.C, _p(self.pc_voxel_id), self.N, _p(self.pc_feature),
                          self.pc_feature.stride(0), s)
         return self.pc_feature
@@ -666,9 +718,10 @@ class SparseUNetEngine:
         else:
             self._side = None
         og = self.out_grad
-        C.gp_memset(_p(og), 0, og.numel() * 4, s)
-        C.gp_scatter_add_rows(_p(self.d_pc_feature), self.d_pc_feature.stride(0), og.shape[1],
-                              _p(self.pc_voxel_id), self.N, _p(og), og.stride(0), s)
+        if self.source == "points":     # sparse-in: the caller wrote the per-voxel gradient into self.out_grad
+            C.gp_memset(_p(og), 0, og.numel() * 4, s)
+            C.gp_scatter_add_rows(_p(self.d_pc_feature), self.d_pc_feature.stride(0), og.shape[1],
+                                  _p(self.pc_voxel_id), self.N, _p(og), og.stride(0), s)
         for op in self._bwd:
             op()
         if self._side is not None:
@@ -689,6 +742,33 @@ class SparseUNetEngine:
         if b1 < self.B + 1:
             self.batch_offsets[b1:] = self.batch_offsets[b1 - 1]
         self.n_loaded = n
+
+    def load_sparse(self, features: Optional[torch.Tensor], indices: torch.Tensor, n=None):
+        """SparseConvTensor in: features [M, C] fp32, indices [M, 4] int32 (batch, x, y, z), M <= max_rows[0], any row
+        order, no duplicates.  n: device int32[1] row count (sync-free callers) or None (= M).  features=None keeps the
+        current input rows (levels_from engines share them)."""
+        if self.levels_owner is not None:
+            raise GapartError("load_sparse on an engine that shares its levels: load the owner")
+        M = indices.shape[0]
+        if indices.dtype != torch.int32 or indices.dim() != 2 or indices.shape[1] != 4 or M > self.max_rows[0]:
+            raise GapartError(f"load_sparse: indices must be int32 [M<={self.max_rows[0]}, 4], got {tuple(indices.shape)}")
+        self.coords[0][:M].copy_(indices, non_blocking=True)
+        if features is not None:
+            if features.shape != (M, self.in_channels):
+                raise GapartError(f"load_sparse: features must be [{M}, {self.in_channels}]")
+            self.vox_feats[:M].copy_(features, non_blocking=True)
+        if n is None:
+            self.d_n[0].fill_(M)
+        else:
+            self.d_n[0].copy_(n.reshape(1), non_blocking=True)
+
+    def check_indices(self):
+        """host sync: raise on out-of-range or duplicate coordinates seen by build_levels() since the last check"""
+        e = int(self.d_err.item())
+        if e:
+            self.d_err.zero_()
+            what = [w for bit, w in ((1, "outside spatial_shape / batch_size"), (2, "duplicated")) if e & bit]
+            raise GapartError("SparseConvTensor indices " + " and ".join(what))
 
     def forward_points(self, points: torch.Tensor, batch_offsets: torch.Tensor) -> torch.Tensor:
         self.load_points(points, batch_offsets)
@@ -715,7 +795,10 @@ class SparseUNetEngine:
         """one host sync: remember the current per-level row counts as launch hints (+25% head-room).
         Call after a representative build_levels(); plans captured in CUDA graphs afterwards use them."""
         counts = self.level_counts()
-        self.check_dropped()
+        if self.source == "points":
+            self.check_dropped()
+        else:
+            self.check_indices()
         self.rows_hint[:] = [int(c * 1.25) + 1 for c in counts]
         return counts
 

@@ -116,6 +116,29 @@ class _EngineBackbone(torch.autograd.Function):
         return None, None, None, torch.zeros((), device=grad.device)
 
 
+class _EngineSparse(torch.autograd.Function):
+    """per-voxel features [M, Cin] -> per-voxel output [M, C0] through a sparse-in engine whose levels are already
+    built (load_sparse + build_levels on the owner); parameter gradients go to the engine's flat arena, the input
+    gradient comes back through autograd (it continues into the differentiable voxel mean and the backbone)."""
+
+    @staticmethod
+    def forward(ctx, feats, engine: SparseUNetEngine):
+        M = feats.shape[0]
+        engine.vox_feats[:M].copy_(feats)
+        out = engine.run_forward()[:M].clone()
+        ctx.engine, ctx.M, ctx.generation = engine, M, engine.fwd_generation
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        eng, M = ctx.engine, ctx.M
+        if ctx.generation != eng.fwd_generation:
+            raise RuntimeError("sparse-in SparseUNetEngine ran another forward before this backward")
+        eng.out_grad[:M].copy_(grad)
+        eng.run_backward()
+        return (eng.in_grad[:M].clone() if eng.in_grad is not None else None), None
+
+
 class GAPartNet(nn.Module):
     def __init__(self, in_channels: int = 6, num_part_classes: int = 10, channels: Sequence[int] = (16, 32, 48, 64, 80, 96, 112),
                  block_repeat: int = 2, ball_query_radius: float = 0.04, max_num_points_per_query: int = 50,
@@ -148,12 +171,31 @@ class GAPartNet(nn.Module):
         self.register_buffer("symmetry_matrix_2", s2, persistent=False)
         self.register_buffer("symmetry_matrix_3", s3, persistent=False)
         self.engine: Optional[SparseUNetEngine] = None
+        self.score_engine: Optional[SparseUNetEngine] = None
+        self.npcs_engine: Optional[SparseUNetEngine] = None
 
     # ------------------------------------------------------------------------------------------
     def attach_engine(self, batch: int, max_points: int, voxel_size: float, spatial_shape=(128, 128, 128), **kw):
         """bind the fused engine to the backbone parameters (call after .to(device))"""
+        max_proposals = kw.pop("max_proposals", None)
         self.engine = SparseUNetEngine(self.backbone, batch=batch, max_points=max_points, spatial_shape=spatial_shape,
                                        voxel_size=voxel_size, in_channels=self.in_channels, **kw)
+        # ScoreNet / NPCS U-Nets (model.py:113-122) on sparse-in engines over the re-voxelised proposals: a proposal is a
+        # "scene" of the 28^3 grid.  Every point joins at most one proposal per clustering: <= 2 * max_points rows, and a
+        # proposal has >= min_num_points_per_proposal points.  Both nets share coordinates and rulebooks.
+        fs = int(self.score_fullscale)
+        rows = 2 * max_points
+        if max_proposals is None:
+            max_proposals = min(rows // max(self.min_num_points_per_proposal, 1), (1 << 32) // (fs * fs * 32) - 1)
+        fea = self.score_head.in_features
+        self.max_proposals = int(max_proposals)
+        self.score_engine = SparseUNetEngine(self.score_unet, batch=self.max_proposals, max_points=1, spatial_shape=(fs,) * 3,
+                                             voxel_size=1.0, in_channels=fea, max_rows=[rows], input_needs_grad=True,
+                                             source="sparse")
+        self.npcs_engine = SparseUNetEngine(self.npcs_unet, batch=self.max_proposals, max_points=1, spatial_shape=(fs,) * 3,
+                                            voxel_size=1.0, in_channels=fea, max_rows=[rows], input_needs_grad=True,
+                                            source="sparse", levels_from=self.score_engine)
+        self._prop_calibrated = False
         return self.engine
 
     def forward_backbone(self, batch: PointBatch) -> torch.Tensor:
@@ -232,6 +274,18 @@ class GAPartNet(nn.Module):
         voxel_tensor = spconv.SparseConvTensor(vf, vcoords.int().contiguous(), spatial_shape=[fs] * 3, batch_size=P)
         if not bool((pc_voxel_id >= 0).all()):
             raise RuntimeError("segmented_voxelize dropped points (the reference traps into pdb here, model.py:328-330)")
+        if self.score_engine is not None:
+            # coordinates, occupancy directory and the three rulebooks of the proposal grid, once for both U-Nets
+            if P > self.max_proposals:
+                raise RuntimeError(f"{P} proposals > max_proposals={self.max_proposals} (attach_engine(max_proposals=...))")
+            eng = self.score_engine
+            eng.active_batch = P           # directory scans cover the proposals that exist, not the static bound
+            eng.load_sparse(None, voxel_tensor.indices)
+            eng.build_levels()
+            if not self._prop_calibrated:
+                eng.calibrate()
+                self.npcs_engine.rows_hint[:] = eng.rows_hint
+                self._prop_calibrated = True
         proposals = dict(valid_mask=valid_mask, sorted_indices=sorted_indices, pt_xyz=pt_xyz, batch_indices=batch_indices,
                          proposal_offsets=prop_off, proposal_indices=prop_idx, num_points_per_proposal=n_per,
                          sem_preds=sem_preds, instance_labels=instance_labels)
@@ -239,7 +293,7 @@ class GAPartNet(nn.Module):
 
     def forward_proposal_score(self, voxel_tensor, pc_voxel_id, proposals):
         off = proposals["proposal_offsets"]
-        feats = self.score_unet(voxel_tensor).features[pc_voxel_id]
+        feats = self._proposal_unet(self.score_unet, self.score_engine, voxel_tensor)[pc_voxel_id]
         pooled, _ = segmented_maxpool(feats, off[:-1], off[1:])
         return self.score_head(pooled)
 
@@ -249,8 +303,16 @@ class GAPartNet(nn.Module):
         proposals["ious"] = ious
         return F.binary_cross_entropy_with_logits(score_logits, get_gt_scores(ious.max(-1)[0], 0.75, 0.25))
 
+    def _proposal_unet(self, unet, engine, voxel_tensor):
+        """score / NPCS U-Net forward on the re-voxelised proposals -> per-voxel features: the fused sparse-in engine
+        when attached (attach_engine), else the per-op spconv-compatible modules"""
+        if engine is None:
+            return unet(voxel_tensor).features
+        engine.training = self.training
+        return _EngineSparse.apply(voxel_tensor.features, engine)
+
     def forward_proposal_npcs(self, voxel_tensor, pc_voxel_id):
-        return self.npcs_head(self.npcs_unet(voxel_tensor).features)[pc_voxel_id]
+        return self.npcs_head(self._proposal_unet(self.npcs_unet, self.npcs_engine, voxel_tensor))[pc_voxel_id]
 
     def loss_proposal_npcs(self, npcs_logits, gt_npcs, proposals):
         sem_preds, sem_labels, prop_idx = proposals["sem_preds"], proposals["sem_labels"], proposals["proposal_indices"]

@@ -133,3 +133,65 @@ def test_engine_eval_mode_uses_running_stats(cuda):
     for (name, bo), bg in zip(o_net.named_buffers(), g_net.buffers()):
         if "running" in name:
             assert torch.equal(bg.cpu(), bo), name
+
+
+@pytest.mark.parametrize("without_stem", [False, True])
+def test_sparse_in_engine_matches_oracle(cuda, without_stem):
+    """SparseConvTensor in (features + indices in ARBITRARY row order, the spconv contract of point_cloud.py:158-162 /
+    model.py:323-327) -> per-voxel output in the caller's row order, parameter and input-feature gradients, against
+    the oracle in fp64; a second engine sharing the levels (the score / NPCS pair) gives the same answer."""
+    import gapartnet_b200.spconv.pytorch as sp
+
+    B, n, voxel, S = 3, 2500, 0.05, 48
+    scs = [synthetic.planes(80 + b, n) for b in range(B)]
+    scenes = []
+    for sc in scs:
+        vf, vc, pcid, rng = ovox.apply_voxelization(sc.points, [voxel] * 3, min_shape=S)
+        scenes.append(dict(vf=vf, vc=vc, pcid=pcid, shape=rng))
+    feats, idx, shape, _ = collate_np(scenes)
+    assert shape == [S, S, S]
+    cin = 16 if without_stem else 6
+    g = torch.Generator().manual_seed(4)
+    M = idx.shape[0]
+    perm = torch.randperm(M, generator=g)
+    f = torch.randn(M, cin, generator=g)
+    f, idx_t = f[perm], torch.from_numpy(idx)[perm]
+    torch.manual_seed(12)
+    chans = [16, 32]
+    o_net = mirror.build_sparse_unet(osp, cin, chans, 2, without_stem=without_stem).double()
+    g_net = mirror.build_sparse_unet(sp, cin, chans, 2, without_stem=without_stem).to(cuda)
+    g_net2 = copy.deepcopy(g_net)
+    sd = {k: v.float() for k, v in o_net.state_dict().items()}
+    g_net.load_state_dict(sd)
+    g_net2.load_state_dict(sd)
+    xo = f.double().clone().requires_grad_(True)
+    yo = o_net(osp.SparseConvTensor(xo, idx_t, shape, B)).features
+    w = torch.randn(16, 3, generator=g, dtype=torch.float64)
+    (yo @ w).square().mean().backward()
+
+    kw = dict(batch=B, max_points=1, spatial_shape=(S, S, S), voxel_size=1.0, in_channels=cin, max_rows=[M + 100],
+              input_needs_grad=True, source="sparse")
+    eng = SparseUNetEngine(g_net, **kw)
+    eng2 = SparseUNetEngine(g_net2, levels_from=eng, **kw)
+    eng.load_sparse(f.to(cuda), idx_t.to(cuda))
+    eng.build_levels()
+    assert eng.calibrate()[0] == M
+    for e in (eng, eng2):
+        e.zero_grad()
+        y = e.run_forward()[:M]
+        assert rel_err(y, yo) < 1e-3
+        yl = y.detach().clone().requires_grad_(True)
+        (yl @ w.float().to(cuda)).square().mean().backward()
+        e.out_grad[:M].copy_(yl.grad)
+        e.run_backward()
+        assert rel_err(e.in_grad[:M], xo.grad) < 1e-3
+        for (name, p64), pg in zip(o_net.named_parameters(), e.net.parameters()):
+            assert rel_err(pg.grad, p64.grad) < 2e-3, name
+    # duplicate / out-of-range coordinates are reported by the device-side flag
+    from gapartnet_b200._lib import GapartError
+    bad = idx_t.clone()
+    bad[1] = bad[0]
+    eng.load_sparse(f.to(cuda), bad.to(cuda))
+    eng.build_levels()
+    with pytest.raises(GapartError):
+        eng.check_indices()
