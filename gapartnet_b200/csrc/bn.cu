@@ -756,6 +756,42 @@ __global__ void __launch_bounds__(256) k_scatter_add_rows(const float* __restric
     }
 }
 
+// backward of the voxel mean (epic_ops.voxelize reduction="mean" is differentiable w.r.t. the point features:
+// grouping_utils.py:93-101 feeds backbone features through it): dP[i,:] = dV[id[i],:] / count[id[i]], 0 for dropped points
+__global__ void __launch_bounds__(256) k_voxel_mean_bwd(const float* __restrict__ dV, int ldv, int C,
+                                                        const int* __restrict__ idx, const int* __restrict__ cnt, int N,
+                                                        float* __restrict__ dP, int ldp) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
+    int cpr = C >> 2;
+    long long total = (long long)N * cpr;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / cpr), cg = (int)(t - (long long)i * cpr);
+        int r = __ldg(idx + i);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r >= 0) {
+            v = ldg4(dV + (size_t)r * ldv + cg * 4);
+            const float w = __fdiv_rn(1.0f, (float)max(__ldg(cnt + r), 1));
+            v.x *= w; v.y *= w; v.z *= w; v.w *= w;
+        }
+        *reinterpret_cast<float4*>(dP + (size_t)i * ldp + cg * 4) = v;
+    }
+}
+
+extern "C" int gp_voxel_mean_bwd(const float* dV, int ldv, int C, const int* pc_voxel_id, const int* voxel_cnt, int N,
+                                 float* dP, int ldp, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(C > 0 && C % 4 == 0 && ldv % 4 == 0 && ldp % 4 == 0, "gp_voxel_mean_bwd: C %% 4 != 0");
+    GP_CHECK_ARG(GP_ALIGNED16(dV) && GP_ALIGNED16(dP), "gp_voxel_mean_bwd: pointers must be 16-byte aligned");
+    if (N == 0) return GP_OK;
+    GP_CUDA(gp_launch(k_voxel_mean_bwd, dim3(ew_grid((long long)N * (C / 4))), dim3(256), 0, stream, dV, ldv, C,
+                      pc_voxel_id, voxel_cnt, N, dP, ldp));
+    gp_note_launch(1);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
 extern "C" int gp_gather_rows(const float* F, int ldf, int C, const int* idx, int N, float* Out,
                               int ldo, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -190,7 +190,8 @@ __device__ __forceinline__ unsigned f2ord(float f) {
 __device__ __forceinline__ float ord2f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
-__global__ void k_cg_min(const float4* __restrict__ pts, int n, unsigned* __restrict__ mn) {
+__global__ void k_cg_min(const float4* __restrict__ pts, int n, const int* __restrict__ d_n, unsigned* __restrict__ mn) {
+    n = gp_rows(d_n, n);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned x = 0xffffffffu, y = 0xffffffffu, z = 0xffffffffu;
     if (i < n) {
@@ -215,8 +216,9 @@ __device__ __forceinline__ int3 cg_cell(float4 p, const unsigned* mn, float inv_
     return c;
 }
 __global__ void k_cg_count(const float4* __restrict__ pts, const int* __restrict__ batch_indices, int n,
-                           const unsigned* __restrict__ mn, float inv_cell, int* __restrict__ keys,
-                           int* __restrict__ counts) {
+                           const int* __restrict__ d_n, const unsigned* __restrict__ mn, float inv_cell,
+                           int* __restrict__ keys, int* __restrict__ counts) {
+    n = gp_rows(d_n, n);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int3 c = cg_cell(pts[i], mn, inv_cell);
@@ -224,93 +226,141 @@ __global__ void k_cg_count(const float4* __restrict__ pts, const int* __restrict
     keys[i] = key;
     atomicAdd(counts + key, 1);
 }
-__global__ void k_cg_fill(const int* __restrict__ keys, int n, const int* __restrict__ starts, int* __restrict__ counts,
-                          int* __restrict__ order) {
+__global__ void k_cg_fill(const int* __restrict__ keys, int n, const int* __restrict__ d_n,
+                          const int* __restrict__ starts, int* __restrict__ counts, int* __restrict__ order) {
+    n = gp_rows(d_n, n);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int key = keys[i];
     int c = atomicAdd(counts + key, -1);        // counts down to 0: slot c-1 of the cell
     order[starts[key] + c - 1] = i;
 }
-#define CG_MAXH 320                         // hit indices a query keeps in local memory (>= the reference's caps 50 / 300)
+#define CG_ROUNDS 16                        // candidate rounds a warp keeps in registers (16 x 32 = 512 candidates)
 
-// visit every candidate of query q (27 cells, label filter, bit-identical radius test of k_ball_query); f(k) per hit
-template <typename F>
-__device__ __forceinline__ void cg_for_hits(const float4* __restrict__ pts, const int* __restrict__ starts,
-                                            const int* __restrict__ order, const float4 c, int b, int lab, int use_labels,
-                                            float radius2, int x0, int x1, int y0, int y1, int z0, int z1, F&& f) {
-    for (int x = x0; x <= x1; ++x)
-        for (int y = y0; y <= y1; ++y) {
-            // the z-run of a (x, y) column is contiguous in the cell order: one range per column
-            const int key0 = ((b * CG + x) * CG + y) * CG + z0;
-            const int jb = starts[key0], je = starts[key0 + (z1 - z0) + 1];
-            for (int j = jb; j < je; ++j) {
-                const int k = order[j];
-                const float4 p = __ldg(pts + k);
-                if (use_labels && __float_as_int(p.w) != lab) continue;
-                float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
-                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d2 < radius2) f(k);
-            }
-        }
+// One WARP per query (queries taken in cell order).  The 27 cells of a query are 9 contiguous runs of the cell-sorted
+// point list (one per (x, y) column); the warp flattens them into one candidate sequence and tests 32 candidates per
+// round with coalesced loads of `order`.  Each lane keeps the hits of its rounds in registers.
+// The reference semantics are "the first `cap` hits in ascending point index" (a linear scan that stops at the cap); the
+// edges only depend on that SET, so a truncated query bisects the index threshold T = cap-th smallest hit index with
+// warp-wide counts (registers + one reduction per step) and unions the hits <= T.  History: the r1 kernel fell back to an
+// O(N/B) ordered scan for truncated queries (42 ms per call when an untrained semantic head predicts one class
+// everywhere); a thread-per-query version with the hit list in local memory still spent 3 ms per call on the bisection's
+// local-memory traffic.  More than CG_ROUNDS*32 candidates (very dense scenes): the same algorithm re-tests the
+// candidates in every bisection step instead of keeping them.
+struct CgRuns {
+    int pre[10];   // prefix of the 9 run lengths (uniform)
+    int jb[9];     // run starts
+};
+
+__device__ __forceinline__ int cg_candidate(const CgRuns& r, int u, const int* __restrict__ order) {
+    // u-th candidate of the flattened runs -> point index
+    int col = 0;
+#pragma unroll
+    for (int c = 1; c < 9; ++c) col += (u >= r.pre[c]) ? 1 : 0;
+    int base = r.jb[0], off = r.pre[0];
+#pragma unroll
+    for (int c = 1; c < 9; ++c)
+        if (col == c) { base = r.jb[c]; off = r.pre[c]; }
+    return __ldg(order + base + (u - off));
 }
 
-// One thread per query.  ONE scan of the 27 cells collects the hit indices (local memory, CG_MAXH).  The reference
-// semantics are "the first `cap` hits in ascending point index" (a linear scan that stops at the cap); the edges only
-// depend on that SET, so a truncated query selects the cap smallest indices by bisecting the index threshold over its
-// collected hits (no second distance pass, no O(N/B) ordered scan: that fallback took 42 ms per call when a random-init
-// semantic head predicts one class everywhere and every query overflows cap = 50).  More than CG_MAXH hits (dense
-// scenes): the bisection re-scans the cells instead.
-__global__ void __launch_bounds__(128) k_cg_cluster(const float4* __restrict__ pts, const int* __restrict__ batch_indices,
-                                                    const int* __restrict__ batch_offsets, int Q, float radius2, int cap,
+__device__ __forceinline__ bool cg_hit(const float4* __restrict__ pts, int k, const float4 c, int lab, int use_labels,
+                                       float radius2) {
+    const float4 p = __ldg(pts + k);
+    if (use_labels && __float_as_int(p.w) != lab) return false;
+    // same expression as the ordered scan (k_ball_query): bit-identical radius test
+    float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y), dz = __fsub_rn(c.z, p.z);
+    float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return d2 < radius2;
+}
+
+__global__ void __launch_bounds__(256) k_cg_cluster(const float4* __restrict__ pts, const int* __restrict__ batch_indices,
+                                                    const int* __restrict__ batch_offsets, int Q,
+                                                    const int* __restrict__ d_n, float radius2, int cap,
                                                     int use_labels, const unsigned* __restrict__ mn, float inv_cell,
                                                     const int* __restrict__ starts, const int* __restrict__ order,
                                                     int* __restrict__ num, int* __restrict__ parent) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    Q = gp_rows(d_n, Q);
     if (t >= Q) return;
-    // queries in cell order: the lanes of a warp sit in the same or adjacent cells and walk (nearly) the same candidate
-    // ranges - broadcast loads instead of 32 scattered ones
-    const int q = order[t];
-    const float4 c = pts[q];
-    const int b = batch_indices[q];
+    const int q = __ldg(order + t);
+    const float4 c = __ldg(pts + q);
+    const int b = __ldg(batch_indices + q);
     const int lab = __float_as_int(c.w);
     const int3 cc = cg_cell(c, mn, inv_cell);
-    const int x0 = max(cc.x - 1, 0), x1 = min(cc.x + 1, CG - 1);
-    const int y0 = max(cc.y - 1, 0), y1 = min(cc.y + 1, CG - 1);
     const int z0 = max(cc.z - 1, 0), z1 = min(cc.z + 1, CG - 1);
-    int h[CG_MAXH];
+    // lane c < 9 owns column (dx, dy) = (c / 3 - 1, c % 3 - 1); columns outside the grid are empty runs
+    int my_b = 0, my_len = 0;
+    if (lane < 9) {
+        const int x = cc.x + lane / 3 - 1, y = cc.y + lane % 3 - 1;
+        if (x >= 0 && x < CG && y >= 0 && y < CG) {
+            const int key0 = ((b * CG + x) * CG + y) * CG + z0;
+            my_b = __ldg(starts + key0);
+            my_len = __ldg(starts + key0 + (z1 - z0) + 1) - my_b;
+        }
+    }
+    CgRuns r;
+    int run = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        r.pre[i] = run;
+        r.jb[i] = __shfl_sync(0xffffffffu, my_b, i);
+        run += __shfl_sync(0xffffffffu, my_len, i);
+    }
+    r.pre[9] = run;
+    const int total = run;
+    const bool fits = total <= CG_ROUNDS * 32;
+
+    int hits[CG_ROUNDS];
     int tot = 0;
-    cg_for_hits(pts, starts, order, c, b, lab, use_labels, radius2, x0, x1, y0, y1, z0, z1, [&](int k) {
-        if (tot < CG_MAXH) h[tot] = k;
-        ++tot;
-    });
-    if (tot <= cap) {
-        for (int i = 0; i < tot; ++i) uf_union(parent, q, h[i]);
+    if (fits) {
+#pragma unroll
+        for (int rd = 0; rd < CG_ROUNDS; ++rd) {
+            hits[rd] = -1;
+            const int u = rd * 32 + lane;
+            if (u < total) {
+                const int k = cg_candidate(r, u, order);
+                if (cg_hit(pts, k, c, lab, use_labels, radius2)) { hits[rd] = k; ++tot; }
+            }
+        }
     } else {
-        // index threshold T = the cap-th smallest hit index: smallest T with #(hits <= T) >= cap
-        int lo = batch_offsets[b], hi = batch_offsets[b + 1] - 1;
-        const bool cached = tot <= CG_MAXH;
-        while (lo < hi) {
+        for (int u = lane; u < total; u += 32)
+            tot += cg_hit(pts, cg_candidate(r, u, order), c, lab, use_labels, radius2) ? 1 : 0;
+    }
+    tot = __reduce_add_sync(0xffffffffu, tot);
+
+    int T = 0x7fffffff;      // union every hit with index <= T
+    if (tot > cap) {
+        int lo = __ldg(batch_offsets + b), hi = __ldg(batch_offsets + b + 1) - 1;
+        while (lo < hi) {    // smallest T with #(hits <= T) >= cap; all operands warp-uniform
             const int mid = (lo + hi) >> 1;
             int cnt = 0;
-            if (cached) {
-                for (int i = 0; i < tot; ++i) cnt += h[i] <= mid;
+            if (fits) {
+#pragma unroll
+                for (int rd = 0; rd < CG_ROUNDS; ++rd) cnt += (hits[rd] >= 0 && hits[rd] <= mid) ? 1 : 0;
             } else {
-                cg_for_hits(pts, starts, order, c, b, lab, use_labels, radius2, x0, x1, y0, y1, z0, z1,
-                            [&](int k) { cnt += k <= mid; });
+                for (int u = lane; u < total; u += 32) {
+                    const int k = cg_candidate(r, u, order);
+                    cnt += (k <= mid && cg_hit(pts, k, c, lab, use_labels, radius2)) ? 1 : 0;
+                }
             }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
             if (cnt >= cap) hi = mid; else lo = mid + 1;
         }
-        if (cached) {
-            for (int i = 0; i < tot; ++i)
-                if (h[i] <= lo) uf_union(parent, q, h[i]);
-        } else {
-            cg_for_hits(pts, starts, order, c, b, lab, use_labels, radius2, x0, x1, y0, y1, z0, z1,
-                        [&](int k) { if (k <= lo) uf_union(parent, q, k); });
-        }
+        T = lo;
         tot = cap;
     }
-    if (num) num[q] = tot;
+    if (fits) {
+#pragma unroll
+        for (int rd = 0; rd < CG_ROUNDS; ++rd)
+            if (hits[rd] >= 0 && hits[rd] <= T && hits[rd] != q) uf_union(parent, q, hits[rd]);
+    } else {
+        for (int u = lane; u < total; u += 32) {
+            const int k = cg_candidate(r, u, order);
+            if (k <= T && k != q && cg_hit(pts, k, c, lab, use_labels, radius2)) uf_union(parent, q, k);
+        }
+    }
+    if (num && lane == 0) num[q] = tot;
 }
 
 static long long cg_cells(int batch) { return (long long)batch * CG * CG * CG; }
@@ -321,13 +371,12 @@ extern "C" long long gp_cluster_grid_ws_ints(int N, int batch) {
     return 2ll * N + 2 * (cg_cells(batch) + 1) + 8 + (long long)((temp + 3) / 4) + 128;   // + 256-byte alignment slack
 }
 
-// gp_cluster with a uniform grid (same results, bit for bit); ws: gp_cluster_grid_ws_ints(N, batch) ints
-extern "C" int gp_cluster_grid(const float* points, int p_stride, int N, const int* batch_indices,
-                               const int* batch_offsets, int batch, float radius, int num_samples, const int* labels,
-                               float* pts4_ws, int* ws, long long ws_ints, int* cc_labels, int* num_points_per_query,
-                               void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    GP_CHECK_ARG(num_samples > 0 && p_stride >= 3 && batch > 0 && radius > 0.f, "gp_cluster_grid: bad arguments");
+// the grid pipeline on already packed (x, y, z, label) points; d_n (optional): device count <= N (sync-free callers:
+// every kernel is launched for N and clips to *d_n).  Shared with proposal.cu.
+int cg_cluster_packed(const float4* pts4, const int* batch_indices, const int* batch_offsets, const int* d_n, int N,
+                      int batch, float radius, int num_samples, int use_labels, int* ws, long long ws_ints,
+                      int* cc_labels, int* num_points_per_query, cudaStream_t stream) {
+    GP_CHECK_ARG(num_samples > 0 && batch > 0 && radius > 0.f, "gp_cluster_grid: bad arguments");
     GP_CHECK_ARG(cg_cells(batch) < (1ll << 30), "gp_cluster_grid: batch too large for the cell directory");
     if (N == 0) return GP_OK;
     const long long cells = cg_cells(batch);
@@ -345,21 +394,35 @@ extern "C" int gp_cluster_grid(const float* points, int p_stride, int N, const i
     // cells 0.1 % larger than the radius: two points closer than the radius are at most one cell apart per axis
     // even after the fp32 rounding of (x - min) / cell
     const float inv_cell = 1.0f / (radius * 1.001f);
-    k_pack_xyzl<<<g, 256, 0, stream>>>(points, p_stride, labels, N, (float4*)pts4_ws);
     k_iota<<<g, 256, 0, stream>>>(cc_labels, N);
     GP_CUDA(cudaMemsetAsync(mn, 0xff, 3 * sizeof(unsigned), stream));
     GP_CUDA(cudaMemsetAsync(counts, 0, (size_t)(cells + 1) * sizeof(int), stream));
-    k_cg_min<<<g, 256, 0, stream>>>((const float4*)pts4_ws, N, mn);
-    k_cg_count<<<g, 256, 0, stream>>>((const float4*)pts4_ws, batch_indices, N, mn, inv_cell, keys, counts);
+    k_cg_min<<<g, 256, 0, stream>>>(pts4, N, d_n, mn);
+    k_cg_count<<<g, 256, 0, stream>>>(pts4, batch_indices, N, d_n, mn, inv_cell, keys, counts);
     GP_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, temp, counts, starts, (int)(cells + 1), stream));
-    k_cg_fill<<<g, 256, 0, stream>>>(keys, N, starts, counts, order);
-    k_cg_cluster<<<gp_cdiv(N, 128), 128, 0, stream>>>((const float4*)pts4_ws, batch_indices, batch_offsets, N,
-                                                      radius * radius, num_samples, labels != nullptr, mn, inv_cell,
-                                                      starts, order, num_points_per_query, cc_labels);
+    k_cg_fill<<<g, 256, 0, stream>>>(keys, N, d_n, starts, counts, order);
+    k_cg_cluster<<<gp_cdiv((long long)N * 32, 256), 256, 0, stream>>>(pts4, batch_indices, batch_offsets, N, d_n,
+                                                                      radius * radius, num_samples, use_labels, mn,
+                                                                      inv_cell, starts, order, num_points_per_query,
+                                                                      cc_labels);
     k_ccl_flatten<<<g, 256, 0, stream>>>(cc_labels, N);
-    gp_note_launch(8);
+    gp_note_launch(7);
     GP_LAUNCH_CHECK();
     return GP_OK;
+}
+
+// gp_cluster with a uniform grid (same results, bit for bit); ws: gp_cluster_grid_ws_ints(N, batch) ints
+extern "C" int gp_cluster_grid(const float* points, int p_stride, int N, const int* batch_indices,
+                               const int* batch_offsets, int batch, float radius, int num_samples, const int* labels,
+                               float* pts4_ws, int* ws, long long ws_ints, int* cc_labels, int* num_points_per_query,
+                               void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(p_stride >= 3, "gp_cluster_grid: bad arguments");
+    if (N == 0) return GP_OK;
+    k_pack_xyzl<<<gp_cdiv(N, 256), 256, 0, stream>>>(points, p_stride, labels, N, (float4*)pts4_ws);
+    gp_note_launch(1);
+    return cg_cluster_packed((const float4*)pts4_ws, batch_indices, batch_offsets, nullptr, N, batch, radius, num_samples,
+                             labels != nullptr, ws, ws_ints, cc_labels, num_points_per_query, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -56,7 +56,7 @@ class SparseUNetEngine:
                  voxel_size: float, in_channels: int, max_rows: Optional[Sequence[int]] = None,
                  input_needs_grad: bool = False, bn_eps: Optional[float] = None, bn_momentum: Optional[float] = None,
                  use_tc: Optional[bool] = None, source: str = "points",
-                 levels_from: Optional["SparseUNetEngine"] = None):
+                 levels_from: Optional["SparseUNetEngine"] = None, grad_arena: Optional[torch.Tensor] = None):
         """source = "points": level 0 comes from voxelising `self.points` (load_points -> build_levels).
         source = "sparse": level 0 is a caller-provided SparseConvTensor (features [M, C] + indices [M, 4] (b,x,y,z) in
         ANY row order, the spconv.SparseConvTensor contract of structure/point_cloud.py:158-162 and model.py:323-327):
@@ -64,7 +64,10 @@ class SparseUNetEngine:
         run_backward consumes a per-voxel gradient (and yields the input-feature gradient if input_needs_grad).
         levels_from = another engine on the SAME coordinates (GAPartNet's score and NPCS U-Nets both run on the
         re-voxelised proposals, model.py:358,392): coordinates, occupancy directories and all rulebooks are shared,
-        only build them once on the owner."""
+        only build them once on the owner.
+        grad_arena = a contiguous fp32 vector with exactly the module's parameter count: the engine's gradients live
+        there (a slice of a model-wide arena: one allreduce / one optimizer launch for everything) instead of in an
+        arena of its own."""
         p0 = next(net.parameters())
         if not p0.is_cuda:
             raise GapartError("SparseUNetEngine needs the module on a CUDA device")
@@ -88,6 +91,7 @@ class SparseUNetEngine:
             raise ValueError(source)
         self.source = source
         self.levels_owner = levels_from
+        self._grad_arena = grad_arena
 
         # ---- level geometry ---------------------------------------------------------------
         chans = list(net.ublock.channels)
@@ -529,7 +533,13 @@ class SparseUNetEngine:
         # one flat fp32 gradient arena (DDP-style: a single allreduce covers every parameter)
         params = list(net.parameters())
         total = sum(p.numel() for p in params)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        if self._grad_arena is not None:
+            ga = self._grad_arena
+            if ga.numel() != total or ga.dtype != torch.float32 or not ga.is_contiguous() or ga.device != self.dev:
+                raise GapartError(f"grad_arena must be a contiguous fp32 vector of {total} elements on {self.dev}")
+            self.flat_grad = ga
+        else:
+            self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self._grad_views = []
         off = 0
         for p in params:
@@ -632,6 +642,27 @@ class SparseUNetEngine:
             ev = torch.cuda.Event()
             ev.record(side)
             self._lvl_events[L + 1] = ev
+
+    def build_levels_external(self, xyz: torch.Tensor, feats: torch.Tensor, batch_offsets: torch.Tensor,
+                              range_min: torch.Tensor, range_max: torch.Tensor):
+        """points-mode engine fed by the caller instead of load_points(): voxelise `feats` [max_points, C] at the
+        coordinates `xyz` [max_points, 3] with a FIXED range (device float[3] each; voxel size = self.voxel_size),
+        scenes given by `batch_offsets` int64 [batch + 1] (rows >= batch_offsets[-1] are ignored), then all
+        rulebooks.  This is segmented_voxelize's epic_ops.voxelize call (grouping_utils.py:93-101): one scene per
+        proposal, range [0, fullscale)^3, voxel size 1.  No host sync."""
+        if self.source != "points" or self.levels_owner is not None:
+            raise GapartError("build_levels_external needs a points-mode engine that owns its levels")
+        if xyz.shape[0] != self.N or feats.shape != (self.N, self.in_channels) or batch_offsets.numel() != self.B + 1:
+            raise GapartError("build_levels_external: buffers must have the engine's static capacity")
+        s = self._bind_stream()
+        g0 = self.grids[0]
+        C.gp_voxelize(_p(xyz), xyz.stride(0), _p(feats), self.in_channels, feats.stride(0), _p(batch_offsets), self.B,
+                      self.N, _p(self.vs), _p(range_min), _p(range_max), 0, *g0.shape, _p(g0.words), _p(g0.prefix),
+                      _p(self.scan_tmp[0]), _p(self.pt_cell), self.max_rows[0], _p(self.vox_feats), _p(self.vox_cnt),
+                      _p(self.coords[0]), _p(self.pc_voxel_id), _p(self.d_n[0]), _p(self.batch_splits), s)
+        C.gp_count_dropped(_p(self.pc_voxel_id), _p(batch_offsets), self.B, self.N, _p(self.d_dropped), s)
+        self._lvl_events = None
+        self._rulebooks(s, range(self.depth))
 
     def _wait_level(self, L: int):
         """forward plan hook: level L's tables (built on the side stream by build_levels(overlap=True)) are ready"""

@@ -1,0 +1,422 @@
+"""The full GAPartNet train step (BASELINE.json configs[3]) as ONE static-shape, sync-free program: capturable in a
+CUDA graph, no host synchronisation between the input copy and the optimizer step.
+
+Reference: GAPartNet._training_or_validation_step (/root/reference/gapartnet/network/model.py:466-659) with
+training_schedule [0, 0] (all five losses), configure_optimizers (:1051-1055, Adam lr 1e-3).
+
+What differs from `GAPartNet.training_step` (the eager mirror of the reference in network/model.py) is only HOW the
+same arithmetic is scheduled:
+  * backbone, ScoreNet U-Net and NPCS U-Net run on SparseUNetEngine instances (fused tcgen05 conv / BN kernels); the two
+    proposal U-Nets share one voxelisation and one set of rulebooks;
+  * the proposal stage is gp_proposals_build (csrc/proposal.cu): static capacities, device-side counts;
+  * every loss is written with masks over static shapes instead of boolean indexing (`x[mask].mean()` becomes
+    `where(mask, x, 0).sum() / mask.sum()`), so no op depends on a data-dependent size;
+  * all parameters live in one flat fp32 arena, all gradients in another (one allreduce, one fused Adam launch).
+tests/test_fused_step_gpu.py pins it against the reference's own step (tests/golden/cfg4_step.npz).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .._lib import C, GapartError
+from ..engine import SparseUNetEngine
+from ..ops import _p
+from ..proposals import ProposalStage
+from .model import GAPartNet, PointBatch
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# autograd glue around the engines (static buffers in, static buffers out)
+# ---------------------------------------------------------------------------------------------------------------------
+class _GatherRows(torch.autograd.Function):
+    """out[i] = feat[idx[i]] (idx int32, static length); backward scatter-adds."""
+
+    @staticmethod
+    def forward(ctx, feat, idx):
+        out = torch.empty(idx.numel(), feat.shape[1], dtype=feat.dtype, device=feat.device)
+        C.gp_gather_rows(_p(feat), feat.stride(0), feat.shape[1], _p(idx), idx.numel(), _p(out), out.stride(0), _stream())
+        ctx.save_for_backward(idx)
+        ctx.n_rows = feat.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = g.contiguous()
+        d = torch.zeros(ctx.n_rows, g.shape[1], dtype=g.dtype, device=g.device)
+        C.gp_scatter_add_rows(_p(g), g.stride(0), g.shape[1], _p(idx), idx.numel(), _p(d), d.stride(0), _stream())
+        return d, None
+
+
+class _BackboneFn(torch.autograd.Function):
+    """points already sit in engine.points: voxelize + rulebooks + U-Net forward -> per-point features"""
+
+    @staticmethod
+    def forward(ctx, anchor, engine: SparseUNetEngine):
+        engine.build_levels(overlap=True)
+        out = engine.run_forward().detach()
+        ctx.engine, ctx.generation = engine, engine.fwd_generation
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.engine
+        if ctx.generation != eng.fwd_generation:
+            raise RuntimeError("backbone engine ran another forward before this backward")
+        eng.d_pc_feature.copy_(g)
+        eng.run_backward()
+        return torch.zeros_like(g[0, 0]), None
+
+
+class _ProposalVoxelize(torch.autograd.Function):
+    """segmented_voxelize's mean-voxelisation (grouping_utils.py:93-101) of the proposal point features onto the
+    fullscale^3 grids + the rulebooks of the proposal U-Nets; differentiable w.r.t. the point features."""
+
+    @staticmethod
+    def forward(ctx, pfeat, stage: ProposalStage, engine: SparseUNetEngine):
+        engine.build_levels_external(stage.sxyz, pfeat, stage.proposal_offsets, stage.range_min, stage.range_max)
+        ctx.engine = engine
+        return engine.vox_feats.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.engine
+        g = g.contiguous()
+        d = torch.empty(eng.N, g.shape[1], dtype=g.dtype, device=g.device)
+        C.gp_voxel_mean_bwd(_p(g), g.stride(0), g.shape[1], _p(eng.pc_voxel_id), _p(eng.vox_cnt), eng.N, _p(d), d.stride(0),
+                            _stream())
+        return d, None, None
+
+
+class _ProposalUNet(torch.autograd.Function):
+    """voxel features (already in the engine's shared input buffer) -> per proposal-point features
+    `unet(voxel_tensor).features[pc_voxel_id]` (model.py:358-359)"""
+
+    @staticmethod
+    def forward(ctx, vox_feats, engine: SparseUNetEngine):
+        out = engine.run_forward().detach()
+        ctx.engine, ctx.generation = engine, engine.fwd_generation
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.engine
+        if ctx.generation != eng.fwd_generation:
+            raise RuntimeError("proposal engine ran another forward before this backward")
+        eng.d_pc_feature.copy_(g)
+        eng.run_backward()
+        return eng.in_grad.detach().clone(), None
+
+
+class _SegMaxPool(torch.autograd.Function):
+    """epic_ops.reduce.segmented_maxpool over static CSR offsets (empty trailing segments give 0 / -1)"""
+
+    @staticmethod
+    def forward(ctx, x, begin, end):
+        S, Cc = begin.numel(), x.shape[1]
+        out = torch.empty(S, Cc, dtype=torch.float32, device=x.device)
+        arg = torch.empty(S, Cc, dtype=torch.int32, device=x.device)
+        C.gp_segmented_reduce(_p(x), x.stride(0), Cc, _p(begin), _p(end), S, 2, _p(out), _p(arg), _stream())
+        ctx.save_for_backward(arg)
+        ctx.n = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        Cc = g.shape[1]
+        ok = arg >= 0
+        flat = arg.clamp(min=0).long() * Cc + torch.arange(Cc, device=g.device)[None, :]
+        dx = torch.zeros(ctx.n * Cc, dtype=g.dtype, device=g.device)
+        dx.index_add_(0, flat.reshape(-1), torch.where(ok, g, torch.zeros_like(g)).reshape(-1))
+        return dx.view(ctx.n, Cc), None, None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# losses over static shapes (masks instead of boolean indexing); same arithmetic as network/losses.py + model.py
+# ---------------------------------------------------------------------------------------------------------------------
+def _masked_mean(x, mask):
+    m = mask.to(x.dtype)
+    return torch.where(mask, x, torch.zeros_like(x)).sum() / m.sum().clamp(min=1.0)
+
+
+def focal_loss_static(logits, targets, gamma: float, ignore_index: int):
+    """losses.py:35-64 (alpha=None, reduction='mean') with the ignore mask applied as a weight"""
+    keep = targets != ignore_index
+    t = targets.clamp(min=0)
+    log_p = F.log_softmax(logits, dim=-1)
+    log_pt = log_p.gather(1, t[:, None]).squeeze(1)
+    loss = -log_pt * (1 - log_pt.exp()) ** gamma
+    return _masked_mean(loss, keep)
+
+
+def dice_loss_static(logits, targets, eps: float = 1e-8):
+    """losses.py:132-158 on [N, C] logits viewed as [N, C, 1, 1] (model.py:186-191): per-point soft dice, mean"""
+    soft = F.softmax(logits, dim=1)
+    onehot = torch.zeros_like(soft).scatter_(1, targets.clamp(min=0)[:, None], 1.0) + 1e-6
+    inter = (soft * onehot).sum(1)
+    card = (soft + onehot).sum(1)
+    return (1.0 - 2.0 * inter / (card + eps)).mean()
+
+
+def gt_scores_static(ious, fg: float = 0.75, bg: float = 0.25):
+    """grouping_utils.py:144-156"""
+    k, b = 1 / (fg - bg), bg / (bg - fg)
+    return torch.where(ious > fg, torch.ones_like(ious), torch.where(ious < bg, torch.zeros_like(ious), ious * k + b))
+
+
+def npcs_group_loss_static(npcs, gt, pidx, mask, mats, max_proposals: int):
+    """compute_npcs_loss (grouping_utils.py:14-43) for one symmetry group over static shapes.
+    npcs, gt [n,3]; pidx [n] proposal ids; mask [n] points of this group; mats [n or 1, m, 3, 3]."""
+    gt_r = (gt[:, None, None, :] @ mats).squeeze(2)                       # n, m, 3
+    dist2 = ((npcs[:, None, :] - gt_r - 0.5) ** 2).sum(-1)                # n, m
+    dist2 = torch.where(mask[:, None], dist2, torch.ones_like(dist2))    # keep sqrt' finite on masked rows
+    loss = torch.where(dist2 <= 0.01, 5 * dist2, torch.sqrt(dist2) - 0.05)
+    loss = torch.where(mask[:, None], loss, torch.zeros_like(loss))
+    m = loss.shape[1]
+    sums = torch.zeros(max_proposals, m, dtype=loss.dtype, device=loss.device).index_add_(0, pidx, loss)
+    cnt = torch.zeros(max_proposals, dtype=loss.dtype, device=loss.device).index_add_(0, pidx, mask.to(loss.dtype))
+    present = cnt > 0
+    per_prop = (sums / cnt.clamp(min=1.0)[:, None]).min(dim=-1)[0]
+    return torch.where(present, per_prop, torch.zeros_like(per_prop)).sum() / present.to(loss.dtype).sum().clamp(min=1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class FusedTrainStep:
+    """net: GAPartNet on a CUDA device (NOT yet attached to engines).  One instance = one static batch geometry:
+    `batch` scenes, exactly `num_points` points in total per step (the reference pads / samples to 20 000 per scene)."""
+
+    def __init__(self, net: GAPartNet, batch: int, num_points: int, voxel_size: float, spatial_shape=(128, 128, 128),
+                 max_proposals: int = 32768, max_instances: int = 64, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 use_graph: bool = True, world_size: int = 1):
+        dev = next(net.parameters()).device
+        if dev.type != "cuda":
+            raise GapartError("FusedTrainStep needs the model on a CUDA device (no CPU fallback)")
+        self.net, self.dev = net, dev
+        self.B, self.N, self.maxP, self.Imax = int(batch), int(num_points), int(max_proposals), int(max_instances)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.world_size = int(world_size)
+        N = self.N
+
+        # ---- one flat parameter arena, one flat gradient arena -------------------------------------------------------
+        params = list(net.parameters())
+        total = sum(p.numel() for p in params)
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        off = 0
+        spans = {}
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self.flat_param[off:off + n].copy_(p.reshape(-1))
+                p.data = self.flat_param[off:off + n].view_as(p)
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+                spans[id(p)] = (off, n)
+                off += n
+
+        def arena_of(module):
+            ps = list(module.parameters())
+            o0 = spans[id(ps[0])][0]
+            n = sum(q.numel() for q in ps)
+            assert spans[id(ps[-1])][0] + ps[-1].numel() == o0 + n, "module parameters are not contiguous in the arena"
+            return self.flat_grad[o0:o0 + n]
+
+        # ---- engines ------------------------------------------------------------------------------------------------
+        fs = int(net.score_fullscale)
+        fea = net.score_head.in_features
+        self.engine = SparseUNetEngine(net.backbone, batch=self.B, max_points=N, spatial_shape=spatial_shape,
+                                       voxel_size=voxel_size, in_channels=net.in_channels, grad_arena=arena_of(net.backbone))
+        net.engine = self.engine
+        kw = dict(batch=self.maxP, max_points=2 * N, spatial_shape=(fs,) * 3, voxel_size=1.0, in_channels=fea,
+                  max_rows=[2 * N], input_needs_grad=True)
+        self.score_engine = SparseUNetEngine(net.score_unet, grad_arena=arena_of(net.score_unet), **kw)
+        self.npcs_engine = SparseUNetEngine(net.npcs_unet, grad_arena=arena_of(net.npcs_unet), levels_from=self.score_engine,
+                                            **kw)
+        self.stage = ProposalStage(N, self.B, self.maxP, dev, radius=net.ball_query_radius,
+                                   cap=net.max_num_points_per_query, cap_shift=net.max_num_points_per_query_shift,
+                                   min_points=net.min_num_points_per_proposal, fullscale=net.score_fullscale,
+                                   scale_max=net.score_scale)
+
+        # ---- static inputs ------------------------------------------------------------------------------------------
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.sem_labels = torch.zeros(N, dtype=torch.int64, device=dev)
+        self.instance_labels = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.instance_centers = torch.zeros(N, 3, **f32)          # instance_regions[:, :3] (model.py:519)
+        self.gt_npcs = torch.zeros(N, 3, **f32)
+        self.num_points_per_instance = torch.zeros(self.B, self.Imax, dtype=torch.int32, device=dev)
+        self.rand = torch.zeros(2, 3, **f32)
+        self.batch_indices = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._arangeN = torch.arange(N, device=dev)
+        self._arange2N = torch.arange(2 * N, device=dev)
+        self._arangeP = torch.arange(self.maxP, device=dev)
+        self.losses: Dict[str, torch.Tensor] = {}
+        self.use_graph = use_graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._warm = 0
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def load(self, batch: PointBatch, rand: Optional[torch.Tensor] = None):
+        """copy one PointBatch into the static input buffers (async on the current stream)"""
+        if batch.points.shape[0] != self.N or batch.batch_size != self.B:
+            raise GapartError(f"FusedTrainStep holds {self.B} scenes / {self.N} points, got {batch.batch_size} / "
+                              f"{batch.points.shape[0]}")
+        e = self.engine
+        e.points.copy_(batch.points, non_blocking=True)
+        e.batch_offsets.copy_(batch.batch_offsets, non_blocking=True)
+        self.sem_labels.copy_(batch.sem_labels, non_blocking=True)
+        self.instance_labels.copy_(batch.instance_labels, non_blocking=True)
+        self.instance_centers.copy_(batch.instance_regions[:, :3], non_blocking=True)
+        self.gt_npcs.copy_(batch.gt_npcs, non_blocking=True)
+        npi = batch.num_points_per_instance
+        if npi.shape[1] > self.Imax:
+            raise GapartError(f"{npi.shape[1]} instances per scene > max_instances={self.Imax}")
+        self.num_points_per_instance.zero_()
+        self.num_points_per_instance[:, :npi.shape[1]].copy_(npi, non_blocking=True)
+        if rand is None:
+            self.rand.uniform_(0.0, 1.0)        # torch.rand(3) twice, grouping_utils.py:86-90
+        else:
+            self.rand.copy_(rand, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def forward_backward(self):
+        """everything between "inputs are in the static buffers" and "gradients are in flat_grad"; no host sync"""
+        net, eng, st = self.net, self.engine, self.stage
+        N, maxP = self.N, self.maxP
+        for e in (eng, self.score_engine, self.npcs_engine):
+            e.training = net.training
+        self.flat_grad.zero_()
+        self.batch_indices.copy_(torch.bucketize(self._arangeN, eng.batch_offsets[1:], right=True))
+        pt_xyz = eng.points[:, :3]
+        anchor = torch.zeros((), device=self.dev, requires_grad=True)
+        pc_feature = _BackboneFn.apply(anchor, eng)
+
+        # ---- heads + dense losses (model.py:160-226, :493-523) --------------------------------------------------------
+        sem_logits = net.sem_seg_head(pc_feature)
+        sem_preds = torch.argmax(sem_logits.detach(), dim=-1)
+        sem_labels, inst = self.sem_labels, self.instance_labels
+        loss_sem = focal_loss_static(sem_logits, sem_labels, 2.0, net.ignore_sem_label) if net.use_sem_focal_loss \
+            else F.cross_entropy(sem_logits, sem_labels, ignore_index=net.ignore_sem_label)
+        if net.use_sem_dice_loss:
+            loss_sem = loss_sem + dice_loss_static(sem_logits, sem_labels)
+        correct = sem_preds == sem_labels
+        all_accu = correct.float().mean()
+        pixel_accu = _masked_mean(correct.float(), sem_labels > 0)
+        offsets = net.offset_head(pc_feature)
+        gt_off = self.instance_centers - pt_xyz
+        valid = (sem_labels > 0) & (inst >= 0)
+        loss_dist = _masked_mean((offsets - gt_off).abs().sum(-1), valid)
+        gt_dir = gt_off / (torch.norm(gt_off, p=2, dim=-1)[:, None] + 1e-8)
+        pr_dir = offsets / (torch.norm(offsets, p=2, dim=-1)[:, None] + 1e-8)
+        loss_dir = _masked_mean(-(gt_dir * pr_dir).sum(-1), valid)
+
+        # ---- proposals (model.py:228-346), sync-free -------------------------------------------------------------------
+        st.build(eng.points, sem_preds, offsets.detach().contiguous(), inst, eng.batch_offsets, self.rand)
+        np_t, p_t = st.counts[st.NP], st.counts[st.P]
+        pp = st.prop_point[:2 * N]
+        ppl = pp.long()
+        pt_mask = self._arange2N < np_t                       # proposal points that exist
+        pr_mask = self._arangeP < p_t                         # proposals that exist
+        pfeat = _GatherRows.apply(pc_feature, pp)
+        vox = _ProposalVoxelize.apply(pfeat, st, self.score_engine)
+        off32 = st.proposal_offsets.int()
+        begin, end = off32[:-1], off32[1:]
+        prop_sem_preds = sem_preds[ppl]
+        prop_sem_labels = sem_labels[ppl]
+
+        # ---- ScoreNet (model.py:348-385, :540-562) ---------------------------------------------------------------------
+        score_feats = _ProposalUNet.apply(vox, self.score_engine)
+        pooled = _SegMaxPool.apply(score_feats, begin, end)
+        score_logits_all = net.score_head(pooled)
+        first = st.prop_point[st.proposal_offsets[:-1].clamp(max=2 * N)].long()
+        plab = sem_labels[first]
+        score_logits = score_logits_all.gather(1, (plab[:, None] - 1).clamp(min=0)).squeeze(1)
+        ious = torch.empty(maxP, self.Imax, dtype=torch.float32, device=self.dev)
+        C.gp_instance_iou(_p(off32), _p(inst[ppl].contiguous()), _p(self.batch_indices[ppl].contiguous()),
+                          _p(self.num_points_per_instance), maxP, self.Imax, _p(ious), _stream())
+        gt_scores = gt_scores_static(ious.max(-1)[0])
+        bce = F.binary_cross_entropy_with_logits(score_logits, gt_scores, reduction="none")
+        loss_score = _masked_mean(bce, pr_mask)
+
+        # ---- NPCS (model.py:387-462) -------------------------------------------------------------------------------------
+        npcs_feats = _ProposalUNet.apply(vox, self.npcs_engine)
+        npcs_logits = net.npcs_head(npcs_feats)                                # head and row gather commute
+        gt = self.gt_npcs[ppl]
+        nvalid = pt_mask & (prop_sem_preds == prop_sem_labels) & (gt != 0).any(dim=-1)
+        cls = (prop_sem_preds - 1).clamp(min=0)
+        npcs = npcs_logits.view(2 * N, -1, 3).gather(1, cls[:, None, None].expand(2 * N, 1, 3)).squeeze(1)
+        sym = net.symmetry_indices[prop_sem_preds.clamp(min=0, max=net.symmetry_indices.numel() - 1)]
+        pidx = st.proposal_indices[:2 * N].long().clamp(max=maxP - 1)
+        loss_npcs = npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym < 3), net.symmetry_matrix_1[sym.clamp(max=2)], maxP)
+        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 3), net.symmetry_matrix_2, maxP)
+        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 4), net.symmetry_matrix_3, maxP)
+
+        loss = loss_sem + loss_dist + loss_dir + loss_score + loss_npcs
+        loss.backward()
+        self.losses = dict(loss=loss.detach(), loss_sem_seg=loss_sem.detach(), loss_offset_dist=loss_dist.detach(),
+                           loss_offset_dir=loss_dir.detach(), loss_prop_score=loss_score.detach(),
+                           loss_prop_npcs=loss_npcs.detach(), all_accu=all_accu, pixel_accu=pixel_accu)
+        self.debug = dict(sem_logits=sem_logits.detach(), offsets=offsets.detach(), sem_preds=sem_preds,
+                          score_logits_all=score_logits_all.detach(), ious=ious, pc_feature=pc_feature.detach())
+
+    def optimizer_step(self):
+        """Adam (torch.optim.Adam defaults: configure_optimizers, model.py:1051-1055) over the flat arenas, one launch;
+        with world_size > 1 the caller all-reduces flat_grad first and grad_scale = 1 / world_size turns the sum
+        into DDP's mean"""
+        self.adam_step.add_(1)
+        C.gp_adam_step(_p(self.flat_param), _p(self.flat_grad), _p(self.adam_m), _p(self.adam_v), self.flat_param.numel(),
+                       self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size, _p(self.adam_step), _stream())
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def calibrate(self):
+        """one host sync after a first eager forward_backward(): row-count hints for the three engines, capacity checks"""
+        self.engine.calibrate()
+        self.score_engine.calibrate()
+        self.npcs_engine.rows_hint[:] = self.score_engine.rows_hint
+        return self.stage.host_counts()
+
+    def capture(self, allreduce=None):
+        """warm up eagerly (2 steps on a side stream, as CUDA graphs require), calibrate, then capture
+        forward_backward [+ allreduce] + optimizer_step in one CUDA graph.  Inputs must be loaded.  Warm-up steps DO
+        update parameters and BatchNorm running statistics, like any training step."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.forward_backward()
+                if allreduce is not None:
+                    allreduce(self.flat_grad)
+                self.optimizer_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        counts = self.calibrate()
+        if self.use_graph:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.forward_backward()
+                if allreduce is not None:
+                    allreduce(self.flat_grad)
+                self.optimizer_step()
+        self._allreduce = allreduce
+        return counts
+
+    def step(self):
+        """one training step on the loaded inputs -> dict of device scalars (read them when you need them)"""
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self.forward_backward()
+            if getattr(self, "_allreduce", None) is not None:
+                self._allreduce(self.flat_grad)
+            self.optimizer_step()
+        return self.losses

@@ -38,6 +38,12 @@ long long gp_launch_count(void);
 int gp_fill_i32(int* p, long long n, int value, void* stream);
 int gp_memset(void* p, int byte, long long nbytes, void* stream);
 
+/* torch.optim.Adam (GAPartNet.configure_optimizers, gapartnet/network/model.py:1051-1055: Adam, lr 1e-3, defaults) over
+ * flat fp32 arenas of n elements in one launch; *d_step = step count t >= 1 (device int, bias correction 1 - beta^t);
+ * grad_scale multiplies the gradient first (1 / world_size after a sum-allreduce = DDP's mean). */
+int gp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                 float beta2, float eps, float grad_scale, const int* d_step, void* stream);
+
 /* ---- occupancy directory ("bitmap-rank perfect hash") ------------------------------------ */
 /* number of uint32 bitmap words for a batch x X x Y x Z grid (-1 if >= 2^32 cells);
  * prefix needs n_words + 1 ints, scan_tmp needs gp_grid_scan_tmp_ints(n_words) ints. */
@@ -194,6 +200,11 @@ int gp_gather_rows(const float* F, int ldf, int C, const int* idx, int N, float*
 int gp_scatter_add_rows(const float* dOut, int ldo, int C, const int* idx, int N, float* dF, int ldf,
                         void* stream);
 
+/* backward of epic_ops.voxelize(reduction="mean") w.r.t. the point features (the proposal branch back-propagates
+ * through it, gapartnet/network/grouping_utils.py:93-101): dP[i,:] = dV[pc_voxel_id[i],:] / voxel_cnt[..], 0 if dropped */
+int gp_voxel_mean_bwd(const float* dV, int ldv, int C, const int* pc_voxel_id, const int* voxel_cnt, int N, float* dP,
+                      int ldp, void* stream);
+
 /* ---- epic_ops: proposal clustering and scoring ------------------------------------------------ */
 /* epic_ops.ball_query.ball_query(points, query, batch_indices, batch_offsets, radius, num_samples,
  * point_labels=, query_labels=) -> (indices [Q,num_samples] i32, num_points_per_query [Q] i32)
@@ -238,6 +249,26 @@ int gp_instance_iou(const int* proposal_offsets, const int* instance_labels, con
 /* epic_ops.nms.nms(ious [P,P], scores, threshold) (gapartnet/network/grouping_utils.py:244): greedy;
  * order = proposal ids by descending score (caller sorts), keep[i] = 1 iff order[i] survives. */
 int gp_nms(const float* ious, int ld, const int* order, int P, float threshold, int* keep, void* stream);
+
+/* GAPartNet.proposal_clustering_and_revoxelize (gapartnet/network/model.py:228-346) + segmented_voxelize up to the scaled
+ * coordinates (gapartnet/network/grouping_utils.py:47-91) as one sync-free pipeline on static buffers:
+ *   valid = (sem_preds > 0) & (instance_labels >= 0)  [instance_labels may be NULL]  -> stable compaction (v2o)
+ *   cluster_proposals on xyz (cap) and on xyz + offsets (cap_shift), same-label ball query + components
+ *   stable sort by component label, both label spaces concatenated, proposals with < min_points points dropped
+ *   per proposal: mean / min / max -> scale -> random placement (rand6 = the two torch.rand(3) draws) -> sxyz
+ * Capacities: N points -> at most 2N proposal points; at most max_proposals proposals (more: cut, CNT_OVERFLOW set).
+ * Outputs: d_counts int[8] = {Nv valid points, Np proposal points, P proposals, overflow (0 or the uncut proposal count), ..};
+ *   v2o[N]; for proposal point t < Np: sorted_indices[t] (index into the valid list = the reference's sorted_indices),
+ *   prop_point[t] = v2o[sorted_indices[t]], proposal_indices[t]; proposal_offsets int64[max_proposals+1] (entries past
+ *   P repeat Np, so it is directly gp_voxelize's batch_offsets with batch = max_proposals); sxyz [2N,3] scaled
+ *   coordinates inside [0, fullscale)^3, bit-identical to the reference's fp32 arithmetic.
+ * ws: gp_proposals_ws_bytes(N, batch, max_proposals) bytes, 256-byte aligned. */
+long long gp_proposals_ws_bytes(int N, int batch, int max_proposals);
+int gp_proposals_build(const float* xyz, int xyz_stride, const int64_t* sem_preds, const float* offsets,
+                       const int* instance_labels, const int64_t* batch_offsets, int batch, int N, float radius, int cap,
+                       int cap_shift, int min_points, float fullscale, float scale_max, const float* rand6,
+                       int max_proposals, void* ws, long long ws_bytes, int* d_counts, int* v2o, int* sorted_indices,
+                       int* prop_point, int* proposal_indices, int64_t* proposal_offsets, float* sxyz, void* stream);
 
 /* ---- pointnet2 (the reference's own CUDA extension `pointnet2_cuda`) ---------------------------- */
 /* Same argument order and meaning as the reference's *_kernel_launcher_fast functions

@@ -90,7 +90,7 @@ def test_full_step_matches_the_reference_step(cuda, gold):
         if key.startswith("grad_full/"):
             name = key.split("/", 1)[1]
             e = _relL2(params[name].grad, g[key])
-            assert e < 2e-2, (name, e)        # relative L2 over the tensor; shallow layers measure ~1e-4
+            assert e < 3e-2, (name, e)        # relative L2 over the tensor (3xTF32 + BatchNorm amplification: see the per-level bars in test_parity_configs_gpu.py)
 
 
 def test_proposal_losses_reach_the_backbone(cuda, gold):
