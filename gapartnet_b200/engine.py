@@ -56,7 +56,8 @@ class SparseUNetEngine:
                  voxel_size: float, in_channels: int, max_rows: Optional[Sequence[int]] = None,
                  input_needs_grad: bool = False, bn_eps: Optional[float] = None, bn_momentum: Optional[float] = None,
                  use_tc: Optional[bool] = None, source: str = "points",
-                 levels_from: Optional["SparseUNetEngine"] = None, grad_arena: Optional[torch.Tensor] = None):
+                 levels_from: Optional["SparseUNetEngine"] = None, grad_arena: Optional[torch.Tensor] = None,
+                 grad_views: Optional[List[torch.Tensor]] = None):
         """source = "points": level 0 comes from voxelising `self.points` (load_points -> build_levels).
         source = "sparse": level 0 is a caller-provided SparseConvTensor (features [M, C] + indices [M, 4] (b,x,y,z) in
         ANY row order, the spconv.SparseConvTensor contract of structure/point_cloud.py:158-162 and model.py:323-327):
@@ -65,9 +66,9 @@ class SparseUNetEngine:
         levels_from = another engine on the SAME coordinates (GAPartNet's score and NPCS U-Nets both run on the
         re-voxelised proposals, model.py:358,392): coordinates, occupancy directories and all rulebooks are shared,
         only build them once on the owner.
-        grad_arena = a contiguous fp32 vector with exactly the module's parameter count: the engine's gradients live
-        there (a slice of a model-wide arena: one allreduce / one optimizer launch for everything) instead of in an
-        arena of its own."""
+        grad_arena + grad_views = the engine's gradients live in a caller-owned arena (a slice of a model-wide one: one
+        allreduce / one optimizer launch for everything): grad_views[i] is the 16-byte aligned view for the i-th
+        parameter of net.parameters(), grad_arena the contiguous slice covering them (padding included)."""
         p0 = next(net.parameters())
         if not p0.is_cuda:
             raise GapartError("SparseUNetEngine needs the module on a CUDA device")
@@ -92,6 +93,7 @@ class SparseUNetEngine:
         self.source = source
         self.levels_owner = levels_from
         self._grad_arena = grad_arena
+        self._grad_views_in = grad_views
 
         # ---- level geometry ---------------------------------------------------------------
         chans = list(net.ublock.channels)
@@ -533,18 +535,22 @@ class SparseUNetEngine:
         # one flat fp32 gradient arena (DDP-style: a single allreduce covers every parameter)
         params = list(net.parameters())
         total = sum(p.numel() for p in params)
+        self._grad_views = []
         if self._grad_arena is not None:
-            ga = self._grad_arena
-            if ga.numel() != total or ga.dtype != torch.float32 or not ga.is_contiguous() or ga.device != self.dev:
-                raise GapartError(f"grad_arena must be a contiguous fp32 vector of {total} elements on {self.dev}")
+            ga, gv = self._grad_arena, self._grad_views_in
+            if gv is None or len(gv) != len(params) or ga.dtype != torch.float32 or ga.device != self.dev:
+                raise GapartError("grad_arena needs one fp32 grad view per parameter on the module's device")
             self.flat_grad = ga
+            for p, v in zip(params, gv):
+                if v.shape != p.shape or v.data_ptr() % 16 or not v.is_contiguous():
+                    raise GapartError("grad_views must be contiguous, 16-byte aligned and shaped like their parameters")
+                self._grad_views.append((p, v))
         else:
             self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        self._grad_views = []
-        off = 0
-        for p in params:
-            self._grad_views.append((p, self.flat_grad[off:off + p.numel()].view_as(p)))
-            off += p.numel()
+            off = 0
+            for p in params:
+                self._grad_views.append((p, self.flat_grad[off:off + p.numel()].view_as(p)))
+                off += p.numel()
         self.bind_grads()
         x0 = _Act(self.vox_feats, 0)
         x0.needs_grad = self.input_needs_grad

@@ -207,9 +207,11 @@ class FusedTrainStep:
         N = self.N
 
         # ---- one flat parameter arena, one flat gradient arena -------------------------------------------------------
+        # (every parameter starts on a 16-byte boundary: the kernels use 128-bit accesses on weights and gradients)
         params = list(net.parameters())
-        total = sum(p.numel() for p in params)
-        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        pad4 = lambda n: (n + 3) & ~3
+        total = sum(pad4(p.numel()) for p in params)
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.adam_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.adam_v = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -223,26 +225,25 @@ class FusedTrainStep:
                 p.data = self.flat_param[off:off + n].view_as(p)
                 p.grad = self.flat_grad[off:off + n].view_as(p)
                 spans[id(p)] = (off, n)
-                off += n
+                off += pad4(n)
 
         def arena_of(module):
             ps = list(module.parameters())
             o0 = spans[id(ps[0])][0]
-            n = sum(q.numel() for q in ps)
-            assert spans[id(ps[-1])][0] + ps[-1].numel() == o0 + n, "module parameters are not contiguous in the arena"
-            return self.flat_grad[o0:o0 + n]
+            o1 = spans[id(ps[-1])][0] + pad4(ps[-1].numel())
+            assert o1 - o0 == sum(pad4(q.numel()) for q in ps), "module parameters are not contiguous in the arena"
+            return dict(grad_arena=self.flat_grad[o0:o1], grad_views=[q.grad for q in ps])
 
         # ---- engines ------------------------------------------------------------------------------------------------
         fs = int(net.score_fullscale)
         fea = net.score_head.in_features
         self.engine = SparseUNetEngine(net.backbone, batch=self.B, max_points=N, spatial_shape=spatial_shape,
-                                       voxel_size=voxel_size, in_channels=net.in_channels, grad_arena=arena_of(net.backbone))
+                                       voxel_size=voxel_size, in_channels=net.in_channels, **arena_of(net.backbone))
         net.engine = self.engine
         kw = dict(batch=self.maxP, max_points=2 * N, spatial_shape=(fs,) * 3, voxel_size=1.0, in_channels=fea,
                   max_rows=[2 * N], input_needs_grad=True)
-        self.score_engine = SparseUNetEngine(net.score_unet, grad_arena=arena_of(net.score_unet), **kw)
-        self.npcs_engine = SparseUNetEngine(net.npcs_unet, grad_arena=arena_of(net.npcs_unet), levels_from=self.score_engine,
-                                            **kw)
+        self.score_engine = SparseUNetEngine(net.score_unet, **arena_of(net.score_unet), **kw)
+        self.npcs_engine = SparseUNetEngine(net.npcs_unet, levels_from=self.score_engine, **arena_of(net.npcs_unet), **kw)
         self.stage = ProposalStage(N, self.B, self.maxP, dev, radius=net.ball_query_radius,
                                    cap=net.max_num_points_per_query, cap_shift=net.max_num_points_per_query_shift,
                                    min_points=net.min_num_points_per_proposal, fullscale=net.score_fullscale,
