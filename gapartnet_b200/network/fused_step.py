@@ -343,8 +343,9 @@ class FusedTrainStep:
         plab = sem_labels[first]
         score_logits = score_logits_all.gather(1, (plab[:, None] - 1).clamp(min=0)).squeeze(1)
         ious = torch.empty(maxP, self.Imax, dtype=torch.float32, device=self.dev)
-        C.gp_instance_iou(_p(off32), _p(inst[ppl].contiguous()), _p(self.batch_indices[ppl].contiguous()),
-                          _p(self.num_points_per_instance), maxP, self.Imax, _p(ious), _stream())
+        prop_inst, prop_batch = inst[ppl].contiguous(), self.batch_indices[ppl].contiguous()   # (named: kept alive)
+        C.gp_instance_iou(_p(off32), _p(prop_inst), _p(prop_batch), _p(self.num_points_per_instance), maxP, self.Imax,
+                          _p(ious), _stream())
         gt_scores = gt_scores_static(ious.max(-1)[0])
         bce = F.binary_cross_entropy_with_logits(score_logits, gt_scores, reduction="none")
         loss_score = _masked_mean(bce, pr_mask)
