@@ -1,17 +1,19 @@
 #!/usr/bin/env python
-"""bench.py - points/sec forward+backward of the GAPartNet sparse U-Net hot path on B200.
+"""bench.py - points/sec forward+backward of the GAPartNet sparse-conv hot path on B200.
 
-Workload (BASELINE.json configs[2], the one `metric` is quoted on): full sparse U-Net backbone
-(in=6, channels [16,32,48,64,80,96,112], block_repeat 2) forward + backward on synthetic
-20 000-point scenes, batch 16 per GPU, voxel 0.02.  One step = voxelize + all 13 rulebooks +
-backbone forward + per-point gather + semantic head/CE loss + full backward (+ NCCL gradient
-allreduce when N > 1).  Weak scaling: every rank processes its own batch of 16 scenes.
+Default workload = BASELINE.json configs[2] (the one `metric` is quoted on): full sparse U-Net backbone (in=6, channels
+[16,32,48,64,80,96,112], block_repeat 2) forward + backward on synthetic 20 000-point scenes, batch 16 per GPU, voxel
+0.02.  One step = voxelize + all 13 rulebooks + backbone forward + per-point gather + semantic head / cross-entropy
+(one fused kernel) + full backward (+ NCCL gradient allreduce inside the captured graph when N > 1).
+Weak scaling: every rank processes its own batch.
 
-  python bench.py --gpus N --steps K --warmup W          (torchrun launches N ranks for N > 1)
-  python bench.py --impl reference ...                   (CPU reference arm: the oracle port)
+  python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
+  python bench.py --workload cfg4                          full GAPartNet train step incl. Adam (BASELINE configs[3])
+  python bench.py --workload cfg5                          200k-point scenes, voxel 0.01, batch 4 (BASELINE configs[4])
+  python bench.py --impl reference ...                     CPU reference arm: the oracle port, same config
 
-Prints ONE JSON line (rank 0).  `value` = points/s with inputs resident in HBM; `e2e` = the same
-step driven from pinned HOST buffers (H2D of the points + D2H of the loss inside the timed region).
+Prints ONE JSON line (rank 0).  `value` = points/s with inputs resident in HBM; `e2e` = the same step driven from pinned
+HOST buffers (H2D of every input + D2H of the loss inside the timed region).
 """
 from __future__ import annotations
 
@@ -32,14 +34,19 @@ CHANNELS = [16, 32, 48, 64, 80, 96, 112]
 BLOCK_REPEAT = 2
 IN_CH = 6
 NUM_CLASSES = 10
-PTS = 20000
-BATCH = 16
-VOXEL = 0.02
-SHAPE = 128
 METRIC = "points/sec fwd+bwd, 20k-pt scenes b16"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the L0 16->16 kernels, from the committed
-# `ncu --set full` captures (profiles/r1_summary.md); null until captured
-TRAFFIC_NCU = {"k_conv_tc": 23642880.0, "k_wgrad_tc": 32341760.0}
+WORKLOADS = {
+    "cfg3": dict(pts=20000, batch=16, voxel=0.02, shape=128, kind="backbone",
+                 name="cfg3: sparse U-Net backbone fwd+bwd (+voxelize, 13 rulebooks, sem head/CE)"),
+    "cfg4": dict(pts=20000, batch=16, voxel=0.02, shape=128, kind="full",
+                 name="cfg4: full GAPartNet train step (backbone + sem/offset heads + dual clustering + 28^3 re-voxelise + "
+                      "ScoreNet + NPCS U-Nets + 5 losses + backward + Adam)"),
+    "cfg5": dict(pts=200000, batch=4, voxel=0.01, shape=256, kind="backbone",
+                 name="cfg5: dense-scene stress, sparse U-Net backbone fwd+bwd (+voxelize, 13 rulebooks, sem head/CE)"),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the L0 16->16 kernels from the committed `ncu --set full`
+# captures (profiles/): a capture, not a live measurement - labelled as such in the JSON line
+TRAFFIC_NCU = {"k_conv_tc": 23642880.0, "k_wgrad_tc": 32341760.0, "source": "ncu --set full capture, profiles/prof_*_r1.metrics.txt"}
 
 
 def _peaks():
@@ -48,6 +55,13 @@ def _peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def shared_config(wl_key: str):
+    """the `config` object both arms print (identical on purpose: the driver compares them)"""
+    wl = WORKLOADS[wl_key]
+    return {"workload": wl["name"], "points_per_scene": wl["pts"], "batch_per_gpu": wl["batch"], "voxel": wl["voxel"],
+            "channels": CHANNELS, "block_repeat": BLOCK_REPEAT}
 
 
 class ClockSampler:
@@ -105,15 +119,11 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def make_batches(n_batches: int, rank: int):
-    """-> list of (points [B*PTS,6] f32, labels [B*PTS] i64) numpy batches of `planes` scenes"""
+def make_scenes(wl, n_batches: int, rank: int):
     from gapartnet_b200 import synthetic
 
-    out = []
-    for j in range(n_batches):
-        scs = [synthetic.planes(3000 + 100000 * rank + 1000 * j + i, PTS) for i in range(BATCH)]
-        out.append((np.concatenate([s.points for s in scs]), np.concatenate([s.sem_labels for s in scs])))
-    return out
+    return [[synthetic.planes(3000 + 100000 * rank + 1000 * j + i, wl["pts"]) for i in range(wl["batch"])]
+            for j in range(n_batches)]
 
 
 def algorithmic_bytes_per_scene(counts_per_level, batch):
@@ -161,121 +171,113 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from gapartnet_b200._lib import C
-    from gapartnet_b200.engine import SparseUNetEngine
     from gapartnet_b200.network import backbone as mirror
+    from gapartnet_b200.network.fused_step import BackboneTrainStep, FusedTrainStep
+    from gapartnet_b200.network.model import GAPartNet, batch_from_scenes
     import gapartnet_b200.spconv.pytorch as sp
 
-    torch.manual_seed(23333)  # gapartnet.yaml:88
-    # (the reference's torch.set_float32_matmul_precision('medium'), gapartnet/train.py:6, only governs the torch
-    #  Linear heads; measured here it makes the 16->10 head GEMMs slower - 7.04 vs 6.89 ms/step - so the heads
-    #  stay on exact-fp32 cuBLAS)
-    net = mirror.build_sparse_unet(sp, IN_CH, CHANNELS, BLOCK_REPEAT).to(dev)
-    head_w = (torch.randn(NUM_CLASSES, CHANNELS[0], device=dev) * 0.1)
-    head_b = torch.zeros(NUM_CLASSES, device=dev)
-    head_gw, head_gb = torch.zeros_like(head_w), torch.zeros_like(head_b)
+    wl = WORKLOADS[args.workload]
+    PTS, BATCH, VOXEL, SHAPE = wl["pts"], wl["batch"], wl["voxel"], wl["shape"]
     N = BATCH * PTS
-    eng = SparseUNetEngine(net, batch=BATCH, max_points=N, spatial_shape=(SHAPE,) * 3, voxel_size=VOXEL,
-                           in_channels=IN_CH)
-    off = torch.arange(BATCH + 1, dtype=torch.int64, device=dev) * PTS
-    eng.batch_offsets.copy_(off)
-
+    torch.manual_seed(23333)  # gapartnet.yaml:88
     n_rot = 4
-    host = make_batches(n_rot, rank)
-    pin_pts = [torch.from_numpy(p).pin_memory() for p, _ in host]
-    pin_lab = [torch.from_numpy(l).pin_memory() for _, l in host]
-    dev_pts = [p.to(dev) for p in pin_pts]
-    dev_lab = [l.to(dev) for l in pin_lab]
-    labels = torch.empty(N, dtype=torch.int64, device=dev)
-    loss_buf = torch.zeros(1, device=dev)
-    loss_host = torch.zeros(1).pin_memory()
+    scenes = make_scenes(wl, n_rot, rank)
+    off = torch.arange(BATCH + 1, dtype=torch.int64, device=dev) * PTS
 
-    def step_body():
-        """voxelize + rulebooks + fwd + sem head/CE + bwd (+ allreduce); everything on the stream."""
-        eng.flat_grad.zero_()
-        eng.build_levels(overlap=True)     # deeper rulebooks + weight packing on a side stream, joined in run_forward
-        feat = eng.run_forward()
-        # semantic head (network/model.py:104,160-166) + cross-entropy, backward written out by hand
-        logits = torch.addmm(head_b, feat, head_w.t())
-        logp = torch.log_softmax(logits, dim=1)
-        loss_buf.copy_(-(logp.gather(1, labels[:, None]).mean()).reshape(1))
-        dlog = torch.softmax(logits, dim=1)
-        dlog.scatter_add_(1, labels[:, None], torch.full((N, 1), -1.0, device=dev))
-        dlog.mul_(1.0 / N)
-        torch.mm(dlog.t(), feat, out=head_gw)
-        head_gb.copy_(dlog.sum(0))
-        torch.mm(dlog, head_w, out=eng.d_pc_feature)
-        eng.run_backward()
+    # ---- the step object and its static input buffers -------------------------------------------------------------------
+    if wl["kind"] == "backbone":
+        net = mirror.build_sparse_unet(sp, IN_CH, CHANNELS, BLOCK_REPEAT).to(dev)
+        head = torch.nn.Linear(CHANNELS[0], NUM_CLASSES).to(dev)
+        step_obj = BackboneTrainStep(net, head, batch=BATCH, num_points=N, voxel_size=VOXEL, spatial_shape=(SHAPE,) * 3,
+                                     in_channels=IN_CH, use_graph=not args.no_graph)
+        eng = step_obj.engine
+        eng.batch_offsets.copy_(off)
+        inputs = {"points": eng.points, "sem_labels": step_obj.labels}
+        host = [{"points": np.concatenate([s.points for s in scs]),
+                 "sem_labels": np.concatenate([s.sem_labels for s in scs])} for scs in scenes]
+        loss_of = lambda: step_obj.loss
+    else:
+        model = GAPartNet(channels=CHANNELS, block_repeat=BLOCK_REPEAT).to(dev)
+        model.train()
+        step_obj = FusedTrainStep(model, batch=BATCH, num_points=N, voxel_size=VOXEL, spatial_shape=(SHAPE,) * 3,
+                                  max_proposals=args.max_proposals, use_graph=not args.no_graph, world_size=world)
+        eng = step_obj.engine
+        net = model.backbone
+        eng.batch_offsets.copy_(off)
+        inputs = {"points": eng.points, "sem_labels": step_obj.sem_labels, "instance_labels": step_obj.instance_labels,
+                  "instance_centers": step_obj.instance_centers, "gt_npcs": step_obj.gt_npcs,
+                  "num_points_per_instance": step_obj.num_points_per_instance}
+        host = []
+        for scs in scenes:
+            b = batch_from_scenes(scs, torch.device("cpu"))
+            npi = np.zeros((BATCH, step_obj.Imax), np.int32)
+            npi[:, :b.num_points_per_instance.shape[1]] = b.num_points_per_instance.numpy()
+            host.append({"points": b.points.numpy(), "sem_labels": b.sem_labels.numpy(),
+                         "instance_labels": b.instance_labels.numpy(),
+                         "instance_centers": np.ascontiguousarray(b.instance_regions[:, :3].numpy()),
+                         "gt_npcs": b.gt_npcs.numpy(), "num_points_per_instance": npi})
+        loss_of = lambda: step_obj.losses["loss"]
 
-    # ---- warm-up eager, then capture the step in a CUDA graph -----------------------------------
-    eng.points.copy_(dev_pts[0])
-    labels.copy_(dev_lab[0])
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(2):
-            step_body()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    counts = eng.calibrate()   # per-level row counts -> split-K launch hints for the deep levels
+    pin = [{k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in h.items()} for h in host]
+    devb = [{k: v.to(dev) for k, v in p.items()} for p in pin]
+    h2d_bytes = int(sum(v.numel() * v.element_size() for v in pin[0].values()))
+    loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def load(src):
+        for k, dst in inputs.items():
+            dst.copy_(src[k], non_blocking=True)
+        if wl["kind"] == "full":
+            step_obj.rand.uniform_(0.0, 1.0)       # torch.rand(3) x 2 of segmented_voxelize (grouping_utils.py:86-90)
+
+    # gradient allreduce (a19): inside the captured graph, on the flat arena (backbone + heads in one call); the sum is
+    # turned into DDP's mean by the optimizer's grad_scale (cfg4) - cfg3/cfg5 have no optimizer in the timed step
+    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+
+    load(devb[0])
+    l0 = C.gp_launch_count()
+    counts = step_obj.capture(allreduce)
+    # launches of OUR kernels in one step: the capture pass issues exactly one step's worth after the two warm-up steps
+    launches_eager = int(C.gp_launch_count() - l0)
+    launches_per_step = launches_eager // 3 if not args.no_graph else launches_eager // 2
+    level_rows = eng.level_counts()
     if args.ncu_step:
-        # exactly one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        step_body()
+        step_obj.forward_backward()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
-        print(json.dumps({"ncu_step": True, "level_rows": counts}))
+        print(json.dumps({"ncu_step": True, "level_rows": level_rows, "workload": args.workload}))
         return
-    use_graph = not args.no_graph
-    graph = None
-    l0 = C.gp_launch_count()
-    if use_graph:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step_body()
-    else:
-        step_body()
-    launches_per_step = int(C.gp_launch_count() - l0)
 
-    # end-to-end feed: pinned host batches are copied by a copy stream into two staging buffers, one step ahead of
-    # the compute stream (every step's H2D happens inside the timed region, like a prefetching DataLoader)
+    # end-to-end feed: pinned host batches are copied by a copy stream into two staging sets, one step ahead of the
+    # compute stream (every step's H2D happens inside the timed region, like a prefetching DataLoader)
     copy_stream = torch.cuda.Stream()
-    stage_pts = [torch.empty_like(dev_pts[0]) for _ in range(2)]
-    stage_lab = [torch.empty_like(dev_lab[0]) for _ in range(2)]
+    stage = [{k: torch.empty_like(v) for k, v in devb[0].items()} for _ in range(2)]
     ev_h2d = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
 
     def h2d(i):
         k, j = i % 2, i % n_rot
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_free[k])          # the compute stream consumed this staging buffer
-            stage_pts[k].copy_(pin_pts[j], non_blocking=True)
-            stage_lab[k].copy_(pin_lab[j], non_blocking=True)
+            copy_stream.wait_event(ev_free[k])          # the compute stream consumed this staging set
+            for name, dst in stage[k].items():
+                dst.copy_(pin[j][name], non_blocking=True)
             ev_h2d[k].record(copy_stream)
 
     def step(i, from_host, last=False):
-        j = i % n_rot
         cur = torch.cuda.current_stream()
         if from_host:
             k = i % 2
             cur.wait_event(ev_h2d[k])
-            eng.points.copy_(stage_pts[k], non_blocking=True)
-            labels.copy_(stage_lab[k], non_blocking=True)
+            load(stage[k])
             ev_free[k].record(cur)
             if not last:
                 h2d(i + 1)
         else:
-            eng.points.copy_(dev_pts[j], non_blocking=True)
-            labels.copy_(dev_lab[j], non_blocking=True)
-        if graph is not None:
-            graph.replay()
-        else:
-            step_body()
-        if world > 1:
-            dist.all_reduce(eng.flat_grad)
-            dist.all_reduce(head_gw)
+            load(devb[i % n_rot])
+        step_obj.step()
         if from_host:
-            loss_host.copy_(loss_buf, non_blocking=True)
+            loss_host.copy_(loss_of().reshape(1).double(), non_blocking=True)
 
     def timed(from_host):
         if from_host:
@@ -309,6 +311,9 @@ def run_ours(args):
         ms_res = timed(False)
     ms_e2e = timed(True)
     loss_val = float(loss_host.item())
+    if wl["kind"] == "full":
+        step_obj.stage.host_counts()       # raises if the proposal capacity overflowed during the run
+    eng.check_dropped()
 
     pts_per_step = N * world
     value = pts_per_step * args.steps / (ms_res / 1e3)
@@ -317,8 +322,9 @@ def run_ours(args):
     # ---- dominant kernels: the L0 SubMConv3d 16->16 launches (forward/dgrad operator k_conv_tc and the weight
     # gradient k_wgrad_tc), timed one by one with CUDA events on the launching stream -------------------------
     roof = None
+    context = None
     if rank == 0:
-        M0 = counts[0]
+        M0 = level_rows[0]
         x = torch.randn(eng.max_rows[0], 16, device=dev)
         y = torch.empty_like(x)
         dyv = torch.randn_like(x)
@@ -330,9 +336,9 @@ def run_ours(args):
         C.gp_conv_tc_fwd(x.data_ptr(), 16, 16, w.data_ptr(), 16, 1, 27 * 16, 0, nbr.data_ptr(), nbr.shape[1], 27,
                          dn.data_ptr(), eng.max_rows[0], y.data_ptr(), 16, 16, 0, None, ws.data_ptr(), M0, st)
 
-        def time_launch(fn):
+        def time_launch(fn, reps=10):
             evs = []
-            for _ in range(3 + 10):
+            for _ in range(3 + reps):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 fn()
@@ -358,15 +364,22 @@ def run_ours(args):
                     "algorithmic_bytes": alg, "peak_source": peak_src}
 
         roof = entry("k_conv_tc (L0 SubMConv3d 16->16 forward; the same kernel runs every dgrad)", t_conv)
-        roof["traffic"] = TRAFFIC_NCU.get("k_conv_tc")
         roof["other_kernels"] = [entry("k_wgrad_tc (L0 SubMConv3d 16->16 weight gradient)", t_wgrad)]
-        roof["other_kernels"][0]["traffic"] = TRAFFIC_NCU.get("k_wgrad_tc")
-        # whole-step algorithmic traffic against the step time
-        per_scene = algorithmic_bytes_per_scene([c / BATCH for c in counts], 1)
+        if args.workload == "cfg3":      # the captures were taken on this workload's level-0 shape
+            roof["traffic"] = TRAFFIC_NCU["k_conv_tc"]
+            roof["other_kernels"][0]["traffic"] = TRAFFIC_NCU["k_wgrad_tc"]
+            roof["traffic_source"] = TRAFFIC_NCU["source"]
+        # whole-step algorithmic traffic of the backbone against the step time
+        per_scene = algorithmic_bytes_per_scene([c / BATCH for c in level_rows], 1)
         wbytes = 12.0 * sum(p.numel() for n_, p in net.named_parameters() if p.dim() == 5)
         step_bytes = per_scene * BATCH + wbytes
         roof["step_algorithmic_GB"] = round(step_bytes / 1e9, 4)
         roof["step_frac"] = round(step_bytes / (ms_res / args.steps / 1e3) / 1e9 / peak, 4)
+
+        if world == 1 and not args.no_cpu_baseline and args.workload == "cfg3":
+            # the two context columns BASELINE.md section 2 promises (labelled; neither is the reference)
+            t_ours = t_conv * 2 + t_wgrad       # fwd + dgrad (same kernel, same table) + wgrad of this layer
+            context = context_baselines(x[:M0], w, dyv[:M0], nbr[:, :M0], time_launch, t_ours, M0)
 
     if rank != 0:
         if world > 1:
@@ -375,44 +388,95 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_points_per_sec(steps=2, warmup=0, scenes=2)
+        cpu = cpu_reference_points_per_sec(wl, steps=1, warmup=0)
 
+    cfg = shared_config(args.workload)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (planes generator, random-init weights seed 23333)",
-        "config": {"workload": "cfg3: sparse U-Net backbone fwd+bwd (+voxelize, 13 rulebooks, sem head/CE)",
-                   "points_per_scene": PTS, "batch_per_gpu": BATCH, "voxel": VOXEL, "channels": CHANNELS,
-                   "block_repeat": BLOCK_REPEAT, "parallelism": f"dp{world}", "cuda_graph": use_graph,
-                   "l2": "per-step working set (activations+tables, >1 GB) exceeds the 126 MB L2; 4 rotating input batches",
-                   "level_rows": counts},
+        "config": cfg,
+        "arm": {"parallelism": f"dp{world}", "cuda_graph": not args.no_graph, "tensor_cores": "tcgen05 3xTF32, fp32 accumulate",
+                "allreduce": "NCCL sum over the flat gradient arena, inside the captured graph" if world > 1 else None,
+                "l2": "per-step working set (activations+tables, >1 GB) exceeds the 126 MB L2; 4 rotating input batches",
+                "level_rows": level_rows, "proposal_counts(Nv,Np,P)": list(counts) if wl["kind"] == "full" else None},
         "clocks": clk.summary(),
         "e2e": {"value": round(e2e_value, 1), "unit": "points/s", "ms_per_step": round(ms_e2e / args.steps, 4),
-                "h2d_bytes_per_step": int(N * IN_CH * 4 + N * 8), "d2h_bytes_per_step": 4, "loss": loss_val},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "loss": loss_val},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "context_baselines": context,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def context_baselines(x, w, dy, nbr, time_launch, t_ours_ms, M0):
+    """BASELINE.md section 2, "timed side by side": one SubMConv3d(16->16, k3) layer forward + backward (BASELINE cfg2 shape
+    at this batch) (i) as a labelled GPU stand-in - torch index_select + mm + add with autograd on the same B200, using the
+    same pair table - because the reference's spconv-CUDA build is not installable here, and (ii) as the PyTorch-CPU
+    dense-conv fallback: torch.nn.functional.conv3d on the densified 128^3 grid, 2 scenes, all host threads."""
+    import torch.nn.functional as F
+
+    out = {}
+    dev = x.device
+    t = nbr.long()
+    pad = x.shape[0]
+    idx = torch.where(t >= 0, t, torch.full_like(t, pad))
+    wk = w.detach().reshape(16, 27, 16).permute(1, 2, 0).contiguous().requires_grad_(True)     # [K, Cin, Cout]
+    xg = x.detach().clone().requires_grad_(True)
+
+    def standin():
+        xp = torch.cat([xg, xg.new_zeros(1, 16)])
+        y = None
+        for k in range(27):
+            c = xp.index_select(0, idx[k]) @ wk[k]
+            y = c if y is None else y + c
+        y.backward(dy)
+        xg.grad = None
+        wk.grad = None
+
+    t_gpu = time_launch(standin, reps=3)
+    out["torch_gpu_standin"] = {
+        "what": "ONE SubMConv3d 16->16 k3 layer fwd+bwd, torch index_select+mm+autograd on this GPU with the same pair "
+                "table (labelled stand-in, NOT the reference: spconv-CUDA is not installable in this image)",
+        "rows": int(M0), "ms": round(t_gpu, 3), "ours_ms": round(t_ours_ms, 4), "ours_speedup": round(t_gpu / t_ours_ms, 1)}
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    scenes_d, S = 2, 128
+    xd = torch.randn(scenes_d, 16, S, S, S, requires_grad=True)
+    wd = torch.randn(16, 16, 3, 3, 3, requires_grad=True)
+    t0 = time.perf_counter()
+    yd = F.conv3d(xd, wd, padding=1)
+    yd.backward(torch.ones_like(yd))
+    t_cpu = time.perf_counter() - t0
+    out["cpu_dense_conv3d"] = {
+        "what": "the same layer as torch.nn.functional.conv3d fwd+bwd on the densified [2,16,128,128,128] grid "
+                "(PyTorch-CPU dense-conv fallback of north_star), all host threads",
+        "scenes": scenes_d, "cores": cores, "s": round(t_cpu, 3), "s_per_scene": round(t_cpu / scenes_d, 3),
+        "ours_ms_per_scene": round(t_ours_ms / 16, 5)}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_points_per_sec(steps: int, warmup: int, scenes: int):
+def cpu_reference_points_per_sec(wl, steps: int, warmup: int, scenes=None):
     """The reference's CPU path for this workload = the oracle port (spconv/epic_ops are not
-    installable here, oracle/__init__.py): numpy voxelize + rulebooks + torch-CPU
-    gather-mm-index_add U-Net forward/backward on `scenes` 20k-point scenes per step."""
+    installable here, oracle/__init__.py): numpy voxelize + rulebooks + torch-CPU gather-mm U-Net
+    forward/backward + sem head/CE on the SAME batch geometry as the GPU arm (scenes per step = batch_per_gpu).
+    For cfg4 this is the backbone + semantic-head part of the step only (said in `sample`)."""
     from gapartnet_b200 import synthetic
     from gapartnet_b200.network import backbone as mirror
     from oracle import spconv_cpu as osp
     from oracle import voxelize as ovox
 
-    # the port's ops are small index_add/mm calls: beyond ~16 threads torch's intra-op pool only
-    # thrashes (measured on the 128-core box: 128 threads were 50x slower than 8), so `cores`
-    # reports the threads actually used
+    PTS, VOXEL, SHAPE = wl["pts"], wl["voxel"], wl["shape"]
+    scenes = wl["batch"] if scenes is None else scenes
+    # the port's ops are index_select/mm calls on <= 140 k rows: beyond ~16 threads torch's intra-op pool only
+    # thrashes (measured on the 128-core box: 128 threads were 50x slower than 8), so `cores` reports the threads used
     cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     torch.manual_seed(23333)
@@ -441,11 +505,12 @@ def cpu_reference_points_per_sec(steps: int, warmup: int, scenes: int):
         return time.perf_counter() - t0
 
     for i in range(warmup):
-        one(9000 + 10 * i)
-    ts = [one(9500 + 10 * i) for i in range(steps)]
+        one(9000 + 100 * i)
+    ts = [one(9500 + 100 * i) for i in range(steps)]
     t = float(np.sum(ts))
+    part = " (backbone + sem head part of the step only)" if wl["kind"] == "full" else ""
     return {"value": round(scenes * PTS * steps / t, 1), "unit": "points/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) x {scenes} scene(s) of {PTS} pts (same graph, voxel {VOXEL}), "
+            "sample": f"{steps} step(s) x {scenes} scene(s) of {PTS} pts (same graph, voxel {VOXEL}){part}, "
                       f"{t / steps:.2f} s/step, torch {torch.get_num_threads()} threads"}
 
 
@@ -454,19 +519,18 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    scenes = 2
+    wl = WORKLOADS[args.workload]
     t0 = time.perf_counter()
-    r = cpu_reference_points_per_sec(steps=args.steps, warmup=args.warmup, scenes=scenes)
+    r = cpu_reference_points_per_sec(wl, steps=args.steps, warmup=args.warmup)
     dt = time.perf_counter() - t0
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(1e3 * scenes * PTS / r["value"], 2), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (planes generator)",
-        "config": {"workload": "cfg3: sparse U-Net backbone fwd+bwd (+voxelize, rulebooks, sem head/CE) - CPU oracle port "
-                               "(spconv/epic_ops are not vendored/installable: oracle/__init__.py)",
-                   "points_per_scene": PTS, "scenes_per_step": scenes, "voxel": VOXEL, "channels": CHANNELS,
-                   "block_repeat": BLOCK_REPEAT},
+        "ms_per_step": round(1e3 * wl["batch"] * wl["pts"] / r["value"], 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (planes generator, random-init weights seed 23333)",
+        "config": shared_config(args.workload),
+        "arm": {"what": "CPU oracle port of the same step (spconv / epic_ops are not vendored or installable: "
+                        "oracle/__init__.py); one process on the host cores whatever --gpus says"},
         "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": round(dt, 1),
@@ -480,6 +544,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--max-proposals", type=int, default=32768, help="cfg4: static proposal capacity per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")

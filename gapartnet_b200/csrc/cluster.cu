@@ -136,7 +136,16 @@ __global__ void k_ccl_hook(const int* __restrict__ offsets, const int* __restric
 __global__ void k_ccl_flatten(int* __restrict__ parent, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    parent[i] = uf_find(parent, i);   // roots are fixed points, so concurrent flattening is safe
+    // READ-ONLY walk (no path halving here): another thread's stale halving store could otherwise overwrite a label
+    // this kernel has already finalised with a non-root ancestor.  Roots are fixed points, so concurrent flattening
+    // with plain stores of the root is safe.
+    volatile int* vp = parent;
+    int r = i, p = vp[r];
+    while (p != r) {
+        r = p;
+        p = vp[r];
+    }
+    parent[i] = r;
 }
 
 extern "C" int gp_ccl(const int* offsets_flat, const int* edges_flat, int num_vertices, int* labels,

@@ -422,3 +422,93 @@ class FusedTrainStep:
                 self._allreduce(self.flat_grad)
             self.optimizer_step()
         return self.losses
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class BackboneTrainStep:
+    """BASELINE.json configs[2] / [4]: sparse U-Net backbone forward + backward on raw points (voxelize + 13 rulebooks
+    inside the step) with the semantic head (nn.Linear(C0, K), model.py:104) and mean cross-entropy (model.py:176-180)
+    as the loss that drives the backward.  No autograd: the head + loss + their backward are ONE kernel
+    (gp_linear_ce) that writes d loss / d pc_feature straight into the engine's gradient input.  Parameters and
+    gradients of backbone + head live in flat arenas (one allreduce).  Capturable in a CUDA graph."""
+
+    def __init__(self, backbone: nn.Module, head: nn.Linear, batch: int, num_points: int, voxel_size: float,
+                 spatial_shape=(128, 128, 128), in_channels: int = 6, ignore_index: int = -100, use_graph: bool = True):
+        dev = next(backbone.parameters()).device
+        if dev.type != "cuda":
+            raise GapartError("BackboneTrainStep needs the modules on a CUDA device (no CPU fallback)")
+        self.dev, self.backbone, self.head = dev, backbone, head
+        self.B, self.N, self.ignore_index = int(batch), int(num_points), int(ignore_index)
+        params = list(backbone.parameters()) + list(head.parameters())
+        pad4 = lambda n: (n + 3) & ~3
+        total = sum(pad4(p.numel()) for p in params)
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self.flat_param[off:off + n].copy_(p.reshape(-1))
+                p.data = self.flat_param[off:off + n].view_as(p)
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+                off += pad4(n)
+        nb = sum(pad4(p.numel()) for p in backbone.parameters())
+        self.engine = SparseUNetEngine(backbone, batch=self.B, max_points=self.N, spatial_shape=spatial_shape,
+                                       voxel_size=voxel_size, in_channels=in_channels, grad_arena=self.flat_grad[:nb],
+                                       grad_views=[p.grad for p in backbone.parameters()])
+        if head.in_features != self.engine.pc_feature.shape[1]:
+            raise GapartError("head.in_features must equal the backbone's output channels")
+        self.labels = torch.zeros(self.N, dtype=torch.int64, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.logits: Optional[torch.Tensor] = None       # set keep_logits() to have the kernel store them
+        self.use_graph = use_graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._allreduce = None
+
+    def keep_logits(self):
+        self.logits = torch.empty(self.N, self.head.out_features, dtype=torch.float32, device=self.dev)
+        return self.logits
+
+    def forward_backward(self):
+        eng, head = self.engine, self.head
+        self.flat_grad.zero_()
+        eng.build_levels(overlap=True)          # deeper rulebooks + weight packing on a side stream
+        feat = eng.run_forward()
+        lg = self.logits
+        C.gp_linear_ce(_p(feat), feat.stride(0), feat.shape[1], _p(self.labels), self.N, _p(head.weight), _p(head.bias),
+                       head.out_features, self.ignore_index, _p(lg), lg.stride(0) if lg is not None else 0,
+                       _p(eng.d_pc_feature), eng.d_pc_feature.stride(0), _p(head.weight.grad),
+                       _p(head.bias.grad) if head.bias is not None else None, _p(self.loss), _p(self._cnt), _stream())
+        eng.run_backward()
+
+    def capture(self, allreduce=None):
+        """2 eager warm-up steps on a side stream (running statistics advance, parameters do not: there is no optimizer
+        in this step), calibration of the row hints, then one CUDA graph of forward_backward [+ allreduce]."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.forward_backward()
+                if allreduce is not None:
+                    allreduce(self.flat_grad)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        counts = self.engine.calibrate()
+        self._allreduce = allreduce
+        if self.use_graph:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.forward_backward()
+                if allreduce is not None:
+                    allreduce(self.flat_grad)
+        return counts
+
+    def step(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self.forward_backward()
+            if self._allreduce is not None:
+                self._allreduce(self.flat_grad)
+        return self.loss

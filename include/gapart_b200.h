@@ -205,6 +205,15 @@ int gp_scatter_add_rows(const float* dOut, int ldo, int C, const int* idx, int N
 int gp_voxel_mean_bwd(const float* dV, int ldv, int C, const int* pc_voxel_id, const int* voxel_cnt, int N, float* dP,
                       int ldp, void* stream);
 
+/* Per-point linear head + mean cross-entropy, forward AND backward in one pass (GAPartNet.sem_seg_head = nn.Linear(16, K),
+ * gapartnet/network/model.py:104,160-166; F.cross_entropy branch of loss_sem_seg, :176-180):
+ *   logits = F W^T + bias (W [K,C] row-major, torch Linear layout); loss = mean over labels != ignore_index of -log softmax;
+ *   logits_out (optional) [N,K]; dF (optional) [N,C] = d loss / d F (overwritten); dW [K,C] / db [K] (optional) are
+ *   ACCUMULATED into; *loss (double, device) is overwritten; d_count_ws: one device int of scratch. C must be 16. */
+int gp_linear_ce(const float* F, int ldf, int C, const int64_t* labels, int N, const float* W, const float* bias, int K,
+                 long long ignore_index, float* logits_out, int ldl, float* dF, int lddf, float* dW, float* db,
+                 double* loss, int* d_count_ws, void* stream);
+
 /* ---- epic_ops: proposal clustering and scoring ------------------------------------------------ */
 /* epic_ops.ball_query.ball_query(points, query, batch_indices, batch_offsets, radius, num_samples,
  * point_labels=, query_labels=) -> (indices [Q,num_samples] i32, num_points_per_query [Q] i32)
