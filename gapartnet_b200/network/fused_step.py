@@ -173,15 +173,23 @@ def gt_scores_static(ious, fg: float = 0.75, bg: float = 0.25):
     return torch.where(ious > fg, torch.ones_like(ious), torch.where(ious < bg, torch.zeros_like(ious), ious * k + b))
 
 
-def npcs_group_loss_static(npcs, gt, pidx, mask, mats, max_proposals: int):
+def npcs_group_loss_static(npcs, gt, pidx, mask, mats, type_idx, max_proposals: int):
     """compute_npcs_loss (grouping_utils.py:14-43) for one symmetry group over static shapes.
-    npcs, gt [n,3]; pidx [n] proposal ids; mask [n] points of this group; mats [n or 1, m, 3, 3]."""
-    gt_r = (gt[:, None, None, :] @ mats).squeeze(2)                       # n, m, 3
+    npcs, gt [n,3]; pidx [n] proposal ids; mask [n] points of this group; mats [T, m, 3, 3] the group's symmetry types,
+    type_idx [n] in [0, T) (None when T == 1).  `gt[:, None, None, :] @ mats[type]` is evaluated as ONE [n,3] x [3, T*m*3]
+    GEMM followed by a gather of the point's type (a broadcast batched matmul over n*m 1x3 @ 3x3 products is what the
+    reference writes, fine on its few thousand masked rows, pathological on the full static capacity)."""
+    T, m = mats.shape[0], mats.shape[1]
+    n = gt.shape[0]
+    g_all = (gt @ mats.permute(2, 0, 1, 3).reshape(3, T * m * 3)).view(n, T, m, 3)
+    if T == 1:
+        gt_r = g_all[:, 0]
+    else:
+        gt_r = g_all.gather(1, type_idx.clamp(0, T - 1)[:, None, None, None].expand(n, 1, m, 3)).squeeze(1)
     dist2 = ((npcs[:, None, :] - gt_r - 0.5) ** 2).sum(-1)                # n, m
     dist2 = torch.where(mask[:, None], dist2, torch.ones_like(dist2))    # keep sqrt' finite on masked rows
     loss = torch.where(dist2 <= 0.01, 5 * dist2, torch.sqrt(dist2) - 0.05)
     loss = torch.where(mask[:, None], loss, torch.zeros_like(loss))
-    m = loss.shape[1]
     sums = torch.zeros(max_proposals, m, dtype=loss.dtype, device=loss.device).index_add_(0, pidx, loss)
     cnt = torch.zeros(max_proposals, dtype=loss.dtype, device=loss.device).index_add_(0, pidx, mask.to(loss.dtype))
     present = cnt > 0
@@ -359,9 +367,9 @@ class FusedTrainStep:
         npcs = npcs_logits.view(2 * N, -1, 3).gather(1, cls[:, None, None].expand(2 * N, 1, 3)).squeeze(1)
         sym = net.symmetry_indices[prop_sem_preds.clamp(min=0, max=net.symmetry_indices.numel() - 1)]
         pidx = st.proposal_indices[:2 * N].long().clamp(max=maxP - 1)
-        loss_npcs = npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym < 3), net.symmetry_matrix_1[sym.clamp(max=2)], maxP)
-        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 3), net.symmetry_matrix_2, maxP)
-        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 4), net.symmetry_matrix_3, maxP)
+        loss_npcs = npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym < 3), net.symmetry_matrix_1, sym, maxP)
+        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 3), net.symmetry_matrix_2, None, maxP)
+        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 4), net.symmetry_matrix_3, None, maxP)
 
         loss = loss_sem + loss_dist + loss_dir + loss_score + loss_npcs
         loss.backward()
