@@ -359,14 +359,33 @@ __global__ void __launch_bounds__(256) k_cg_cluster(const float4* __restrict__ p
         T = lo;
         tot = cap;
     }
+    // Warp-aggregated unions: all lanes link INTO the same vertex q, so naive per-lane uf_union(q, k) calls fight over
+    // parent[root(q)] (one compare-and-swap wins, 31 lanes retry with fresh finds: measured 15 ms per call).  Per round
+    // every lane finds the root of its own hit, the warp agrees on the smallest root m among them and root(q), and each
+    // lane hooks ITS root under m - distinct addresses, no retries in the common case.
+    auto union_round = [&](int k, bool has) {
+        const int rq = uf_find(parent, q);
+        const int r = has ? uf_find(parent, k) : 0x7fffffff;
+        const int m = min(rq, __reduce_min_sync(0xffffffffu, r));
+        if (has && r != m) uf_union(parent, m, r);
+        if (lane == 0 && rq != m) uf_union(parent, m, rq);
+    };
     if (fits) {
 #pragma unroll
-        for (int rd = 0; rd < CG_ROUNDS; ++rd)
-            if (hits[rd] >= 0 && hits[rd] <= T && hits[rd] != q) uf_union(parent, q, hits[rd]);
+        for (int rd = 0; rd < CG_ROUNDS; ++rd) {
+            const bool has = hits[rd] >= 0 && hits[rd] <= T && hits[rd] != q;
+            if (__any_sync(0xffffffffu, has)) union_round(hits[rd], has);
+        }
     } else {
-        for (int u = lane; u < total; u += 32) {
-            const int k = cg_candidate(r, u, order);
-            if (k <= T && k != q && cg_hit(pts, k, c, lab, use_labels, radius2)) uf_union(parent, q, k);
+        for (int u0 = 0; u0 < total; u0 += 32) {
+            const int u = u0 + lane;
+            int k = -1;
+            bool has = false;
+            if (u < total) {
+                k = cg_candidate(r, u, order);
+                has = k <= T && k != q && cg_hit(pts, k, c, lab, use_labels, radius2);
+            }
+            if (__any_sync(0xffffffffu, has)) union_round(k, has);
         }
     }
     if (num && lane == 0) num[q] = tot;

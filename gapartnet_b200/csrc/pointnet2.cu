@@ -245,16 +245,180 @@ static int ref_opt_n_threads(int work_size) {
     return p;
 }
 
+// ---- cluster version: one thread-block cluster of 8 or 16 CTAs per batch element -------------------------------------------
+// The reference kernel (and the single-CTA kernel above) walks ALL points of a batch element from ONE SM every round:
+// at 80 000 points that is 1.3 MB through one SM's L2 port per round, 14-19 us x 20 000 rounds.  Here the points are
+// split over the CTAs of a cluster; each CTA keeps its slice (coordinates + running min distance) in REGISTERS, a
+// round is: local arg-max -> warp shuffles -> one block barrier -> the CTA's candidate (distance, tie key, index, xyz)
+// is written into the shared memory of every CTA of the cluster (DSMEM) -> ONE cluster barrier -> every warp reduces
+// the cluster's candidates on its own.  The winner's coordinates travel with the candidate, so no global load sits on the
+// round's critical path.  Candidate slots are double buffered by round parity: a CTA can only overwrite a slot two
+// rounds later, i.e. after a cluster barrier that every reader of the slot has passed.
+// The arg-max order (distance, bit-reversed reference slot, index) is total, so any reduction topology selects the
+// reference's winner: results stay bit-identical to sampling_gpu.cu:93-209 (tests/test_pointnet2_gpu.py).
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+struct FpsCand { float d; int key; int k; float x, y, z; };
+
+template <int PPT, int FPSC_CL>
+__global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, int bs_ref,
+                                                                 const float* __restrict__ dataset,
+                                                                 float* __restrict__ temp, int* __restrict__ idxs) {
+    if (m <= 0) return;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ float s_xyz[];                 // [PPT * FPS_THREADS][3] this CTA's coordinates (winner lookup)
+    __shared__ float s_d[32];
+    __shared__ int s_key[32], s_k[32];
+    __shared__ FpsCand s_cl[2][FPSC_CL];
+    const int rank = (int)cluster.block_rank(), batch = blockIdx.x / FPSC_CL;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    dataset += (size_t)batch * n * 3;
+    temp += (size_t)batch * n;
+    idxs += (size_t)batch * m;
+    const int base = rank * (PPT * FPS_THREADS);
+    float px[PPT], py[PPT], pz[PPT], pt[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const int k = base + u * FPS_THREADS + tid;
+        if (k < n) {
+            px[u] = dataset[k * 3]; py[u] = dataset[k * 3 + 1]; pz[u] = dataset[k * 3 + 2];
+            pt[u] = temp[k];
+        } else {
+            px[u] = py[u] = pz[u] = 0.f;
+            pt[u] = -1.f;
+        }
+        float* sp = s_xyz + (size_t)(u * FPS_THREADS + tid) * 3;
+        sp[0] = px[u]; sp[1] = py[u]; sp[2] = pz[u];
+    }
+    float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];      // the first sample is point 0
+    if (rank == 0 && tid == 0) idxs[0] = 0;
+    cluster.sync();
+    for (int j = 1; j < m; ++j) {
+        float best = -1.f;
+        int bk = 0, bkey = 0;
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const int k = base + u * FPS_THREADS + tid;
+            if (k < n) {
+                float x2 = px[u], y2 = py[u], z2 = pz[u];
+                float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+                float d2 = min(d, pt[u]);
+                pt[u] = d2;
+                int key = fps_key(k, bs_ref);
+                if (fps_better(d2, key, k, best, bkey, bk)) { best = d2; bk = k; bkey = key; }
+            }
+        }
+        // the reference starts every thread at (best=-1, besti=0): an idle thread contributes point 0
+        if (best < 0.f) { bk = 0; bkey = 0; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float od = __shfl_xor_sync(0xffffffffu, best, o);
+            int okey = __shfl_xor_sync(0xffffffffu, bkey, o);
+            int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (fps_better(od, okey, ok, best, bkey, bk)) { best = od; bkey = okey; bk = ok; }
+        }
+        if (lane == 0) { s_d[wid] = best; s_key[wid] = bkey; s_k[wid] = bk; }
+        __syncthreads();
+        const int par = j & 1;
+        if (wid == 0) {
+            best = s_d[lane]; bkey = s_key[lane]; bk = s_k[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float od = __shfl_xor_sync(0xffffffffu, best, o);
+                int okey = __shfl_xor_sync(0xffffffffu, bkey, o);
+                int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (fps_better(od, okey, ok, best, bkey, bk)) { best = od; bkey = okey; bk = ok; }
+            }
+            // every lane holds the CTA's winner; lane r publishes it to CTA r of the cluster
+            if (lane < FPSC_CL) {
+                FpsCand c;
+                c.d = best; c.key = bkey; c.k = bk;
+                const int loc = bk - base;
+                if (loc >= 0 && loc < PPT * FPS_THREADS) {
+                    c.x = s_xyz[(size_t)loc * 3]; c.y = s_xyz[(size_t)loc * 3 + 1]; c.z = s_xyz[(size_t)loc * 3 + 2];
+                } else {          // an all-idle CTA contributes point 0 (never wins against a real candidate with d >= 0
+                    c.x = dataset[0]; c.y = dataset[1]; c.z = dataset[2];   // unless it ties at (d, key 0, k 0) = itself)
+                }
+                FpsCand* dst = cluster.map_shared_rank(&s_cl[par][rank], lane);
+                *dst = c;
+            }
+        }
+        cluster.sync();
+        FpsCand c;
+        c.d = -2.f; c.key = 0; c.k = 0; c.x = c.y = c.z = 0.f;
+        if (lane < FPSC_CL) c = s_cl[par][lane];
+        int src = lane;
+#pragma unroll
+        for (int o = FPSC_CL / 2; o > 0; o >>= 1) {
+            float od = __shfl_xor_sync(0xffffffffu, c.d, o);
+            int okey = __shfl_xor_sync(0xffffffffu, c.key, o);
+            int ok = __shfl_xor_sync(0xffffffffu, c.k, o);
+            int osrc = __shfl_xor_sync(0xffffffffu, src, o);
+            if (fps_better(od, okey, ok, c.d, c.key, c.k)) { c.d = od; c.key = okey; c.k = ok; src = osrc; }
+        }
+        const int win = __shfl_sync(0xffffffffu, src, 0);
+        const int old = __shfl_sync(0xffffffffu, c.k, 0);
+        x1 = __shfl_sync(0xffffffffu, c.x, win);
+        y1 = __shfl_sync(0xffffffffu, c.y, win);
+        z1 = __shfl_sync(0xffffffffu, c.z, win);
+        if (rank == 0 && tid == 0) idxs[j] = old;
+    }
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const int k = base + u * FPS_THREADS + tid;
+        if (k < n) temp[k] = pt[u];
+    }
+    cluster.sync();    // nobody leaves while its candidate slots may still be written
+}
+
+template <int PPT, int FPSC_CL>
+static int fps_cluster_launch(int b, int n, int m, int bs_ref, const float* dataset, float* temp, int* idxs,
+                              cudaStream_t stream) {
+    const size_t smem = (size_t)PPT * FPS_THREADS * 3 * sizeof(float);
+    GP_CUDA(cudaFuncSetAttribute(k_pn2_fps_cluster<PPT, FPSC_CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (FPSC_CL > 8)
+        GP_CUDA(cudaFuncSetAttribute(k_pn2_fps_cluster<PPT, FPSC_CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(b * FPSC_CL);
+    cfg.blockDim = dim3(FPS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = FPSC_CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GP_CUDA(cudaLaunchKernelEx(&cfg, k_pn2_fps_cluster<PPT, FPSC_CL>, n, m, bs_ref, dataset, temp, idxs));
+    return GP_OK;
+}
+
 extern "C" int gp_pn2_furthest_point_sampling(int b, int n, int m, const float* dataset, float* temp, int* idxs,
                                               void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(b >= 0 && n > 0 && m >= 0, "gp_pn2_furthest_point_sampling: bad sizes");
     if (b == 0 || m == 0) return GP_OK;
     int bs_ref = ref_opt_n_threads(n);
-    if (n <= FPS_THREADS * FPS_PPT)
+    // registers: 1024 threads per CTA leave 64 registers per thread = at most 8 points (xyz + distance) per thread.
+    // 8 CTAs (portable cluster size) cover 65 536 points, 16 CTAs (non-portable, one GPC) 131 072.
+    const int per8 = gp_cdiv(n, 8 * FPS_THREADS), per16 = gp_cdiv(n, 16 * FPS_THREADS);
+    int rc = GP_OK;
+    if (n > 2048 && per16 <= 8) {
+        if (per8 <= 1) rc = fps_cluster_launch<1, 8>(b, n, m, bs_ref, dataset, temp, idxs, stream);
+        else if (per8 <= 2) rc = fps_cluster_launch<2, 8>(b, n, m, bs_ref, dataset, temp, idxs, stream);
+        else if (per8 <= 4) rc = fps_cluster_launch<4, 8>(b, n, m, bs_ref, dataset, temp, idxs, stream);
+        else if (per8 <= 6) rc = fps_cluster_launch<6, 8>(b, n, m, bs_ref, dataset, temp, idxs, stream);
+        else if (per16 <= 4) rc = fps_cluster_launch<4, 16>(b, n, m, bs_ref, dataset, temp, idxs, stream);
+        else if (per16 <= 6) rc = fps_cluster_launch<6, 16>(b, n, m, bs_ref, dataset, temp, idxs, stream);
+        else rc = fps_cluster_launch<8, 16>(b, n, m, bs_ref, dataset, temp, idxs, stream);
+        if (rc) return rc;
+    } else if (n <= FPS_THREADS * FPS_PPT) {
         k_pn2_fps<true><<<b, FPS_THREADS, 0, stream>>>(n, m, bs_ref, dataset, temp, idxs);
-    else
+    } else {
         k_pn2_fps<false><<<b, FPS_THREADS, 0, stream>>>(n, m, bs_ref, dataset, temp, idxs);
+    }
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
