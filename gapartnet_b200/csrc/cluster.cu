@@ -35,16 +35,23 @@ __global__ void k_pack_xyzl(const float* __restrict__ xyz, int stride, const int
 // One thread per query; the warp's queries are consecutive points of (almost always) one scene, so the
 // float4 (x,y,z,label) stream of that scene is a broadcast load per warp.  MODE 0 writes the neighbour
 // table, MODE 1 unions on the fly (fused clustering).
+// parent[] reads go through L1 (ld.global.ca), NOT volatile/L2: with one semantic class per scene (an untrained head)
+// a scene is one giant component and every find of every thread ends on the same root word - as L2-only loads those
+// hot lines serialised the whole kernel (measured 14.5 ms per call for 170 M root reads; 3 ms with a third of them).
+// A stale L1 copy is harmless: links are only created at roots and always towards the smaller index, so a stale parent
+// is still an ancestor, a stale "root" only makes the compare-and-swap below fail (atomics bypass L1) and hand back the
+// fresh parent.  L1 is invalidated at kernel boundaries, so the flatten kernel sees the final forest.
+__device__ __forceinline__ int uf_ld(const int* p) {
+    int v;
+    asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ int uf_find(int* parent, int i) {
-    // volatile: other threads re-link roots concurrently, a stale read only costs another hop.  Path halving: a node
-    // is re-pointed at its grandparent on the way up.  Links are only ever created at roots and always towards the
-    // smaller index, so an ancestor stays an ancestor and the plain (racy) store can only shorten a chain - without it
-    // the "one class everywhere" components of an untrained network (15 k points each) made every find walk long chains
-    volatile int* vp = parent;
-    int p = vp[i];
+    // Path halving: a node is re-pointed at its grandparent on the way up; the plain (racy) store can only shorten a chain
+    int p = uf_ld(parent + i);
     while (p != i) {
-        const int gp = vp[p];
-        if (gp != p) vp[i] = gp;
+        const int gp = uf_ld(parent + p);
+        if (gp != p) parent[i] = gp;
         i = p;
         p = gp;
     }

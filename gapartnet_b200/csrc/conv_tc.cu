@@ -42,13 +42,12 @@
 
 #define TC_ROWS 128
 #define TC_KCHUNK 32                      // floats per chunk
-#define TC_GROUPS 2                       // feeder groups; TMEM A stages = TC_GROUPS * spg (1 or 2 per group)
-#define TC_FEED_WARPS (4 * TC_GROUPS)
-#define TC_WARP_MMA (4 + TC_FEED_WARPS)
-#define TC_WARP_LOAD (TC_WARP_MMA + 1)
-#define TC_THREADS (32 * (TC_WARP_LOAD + 1))
 #define TC_MAX_TAPS 27
 #define TC_TMEM_COLS 512
+// feeder groups G (template parameter; TMEM A stages = G * spg, 1 or 2 per group); warps: 4 epilogue + 4*G feeders +
+// MMA + loader.  G = 2 gathers from global memory with two register sets per thread (128 registers: a third group
+// does not fit); G = 3 is the shared-memory window variant below (one register set, 113 registers available).
+#define TC_THREADS_OF(G) (32 * (4 + 4 * (G) + 2))
 
 // trace slot = sequence number of the chunk within CTA 0 (quadrant-1 warp of every feeder group + the MMA warp)
 #define TC_TS(ev, g) do { if (p.ts && blockIdx.x == 0 && lane == 0 && (g) < 256) p.ts[(ev) * 256 + (g)] = clock64(); } while (0)
@@ -151,6 +150,9 @@ struct TcParams {
     int* zero_sync;  // != NULL: split-K launch zeroes its own output rows (epilogue warps, before the first reduction)
                      // and synchronises the grid through these two counters {zeroed CTAs, finished CTAs}
     long long* ts;   // optional timestamp trace [6][256] of CTA 0 (perf experiments)
+    // shared-memory window variant (WIN): win[2 * tile] = first row, win[2 * tile + 1] = row count of the contiguous
+    // row range of X that holds (nearly) all neighbours of the tile; win_bytes = bytes of one window buffer
+    const int* win; int win_cap; int win_bytes;
 };
 
 __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const float* v) {
@@ -161,14 +163,34 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const float* 
         : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// WIN: the rows of a level are in lexicographic (b,x,y,z) order, so the 27 neighbours of 128 consecutive rows lie in a
+// CONTIGUOUS range of ~3-5 x-planes (300-500 rows at levels 0-2).  The loader brings that range into shared memory with
+// one bulk copy per tile (double buffered, same barrier as the tile's index table) and the feeders gather from shared
+// memory: ~3x less L2->SM traffic than fetching every (row, tap) pair from L2 (each input row is used by ~11 outputs),
+// and - the point - a 30-cycle instead of an ~800-cycle gather latency, so a feeder thread needs ONE register set
+// instead of two and a third feeder group fits.  Neighbours outside the window (range longer than the buffer) fall back
+// to the global load.
+template <int G, bool WIN>
+__global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams p) {
+    constexpr int TC_GROUPS = G;
+    constexpr int TC_FEED_WARPS = 4 * G;
+    constexpr int TC_WARP_MMA = 4 + TC_FEED_WARPS;
+    constexpr int TC_WARP_LOAD = TC_WARP_MMA + 1;
+    constexpr int TC_THREADS = TC_THREADS_OF(G);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int Cout = p.Cout;
     const uint32_t b_bytes = (uint32_t)Cout * 256;            // hi + lo weight image of one chunk
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;                                                                 // [SB] weight images
     const int SB = TC_GROUPS * p.spg;
-    int* s_idx = reinterpret_cast<int*>(tiles + (size_t)SB * b_bytes);                     // [2][Ktaps][128]
+    uint8_t* s_win = tiles + (size_t)SB * b_bytes;                                         // [2][win_bytes] (WIN)
+    int* s_idx = reinterpret_cast<int*>(s_win + (WIN ? 2 * (size_t)p.win_bytes : 0));      // [2][Ktaps][128]
     double* s_stats = reinterpret_cast<double*>(s_idx + 2 * p.Ktaps * TC_ROWS);            // [2][Cout]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + 2 * Cout);
     const int SA = TC_GROUPS * p.spg;             // ring depth of both operands: TMEM A stages and weight images
@@ -179,6 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
     uint64_t* idx_full = acc_empty + 2;           // [2]   neighbour-index tile of a work item landed
     uint64_t* idx_empty = idx_full + 2;           // [2]   every feeder warp is done with the index tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(idx_empty + 2);
+    int* s_wmeta = reinterpret_cast<int*>(tmem_slot + 2);     // [2][2] first row / row count of the window buffers
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ksplit = p.ksplit;
@@ -237,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
         const uint32_t t_quad = tmem_base + ((uint32_t)(32 * quad) << 16) + a_base;
         const int spg = p.spg;
 
-        struct Cur { int w, titer, c, c1, row0; uint32_t idx_a; bool valid, full; };
+        struct Cur { int w, titer, c, c1, row0, wlo, wlen; uint32_t idx_a, win_a; bool valid, full; };
         // enter work item (w, titer) at chunk offset `over` from its first chunk; skips items the group has no
         // chunk in (their index tile is still released: every feeder warp arrives once per work item)
         auto enter = [&](Cur& k, int over) {
@@ -252,6 +275,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                     k.full = (tile + 1) * TC_ROWS <= n_out;
                     k.idx_a = smem_u32(s_idx + (k.titer & 1) * n_idx + rloc0);
                     if (use_tbl) mbar_wait_warp(&idx_full[k.titer & 1], (k.titer >> 1) & 1, lane);
+                    if (WIN) {
+                        k.wlo = s_wmeta[(k.titer & 1) * 2];
+                        k.wlen = s_wmeta[(k.titer & 1) * 2 + 1];
+                        k.win_a = smem_u32(s_win + (size_t)(k.titer & 1) * p.win_bytes);
+                    }
                     k.valid = true;
                     return;
                 }
@@ -311,12 +339,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                     if (!row_ok || !okR) iR[s] = -1;
                 }
             }
+            if (WIN) {
+                const uint32_t oL = (uint32_t)(XL - Xb), oR = (uint32_t)(XR - Xb);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                vL[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-                vR[s] = vL[s];
-                if (iL[s] >= 0) vL[s] = ldg4(reinterpret_cast<const float*>(XL + (uint64_t)(uint32_t)iL[s] * ld_bytes));
-                if (iR[s] >= 0) vR[s] = ldg4(reinterpret_cast<const float*>(XR + (uint64_t)(uint32_t)iR[s] * ld_bytes));
+                for (int s = 0; s < 4; ++s) {
+                    vL[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vR[s] = vL[s];
+                    if (iL[s] >= 0) {
+                        const uint32_t loc = (uint32_t)(iL[s] - k.wlo);
+                        vL[s] = loc < (uint32_t)k.wlen ? lds_f32x4(k.win_a + loc * ld_bytes + oL)
+                                                       : ldg4(reinterpret_cast<const float*>(XL + (uint64_t)(uint32_t)iL[s] * ld_bytes));
+                    }
+                    if (iR[s] >= 0) {
+                        const uint32_t loc = (uint32_t)(iR[s] - k.wlo);
+                        vR[s] = loc < (uint32_t)k.wlen ? lds_f32x4(k.win_a + loc * ld_bytes + oR)
+                                                       : ldg4(reinterpret_cast<const float*>(XR + (uint64_t)(uint32_t)iR[s] * ld_bytes));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    vL[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vR[s] = vL[s];
+                    if (iL[s] >= 0) vL[s] = ldg4(reinterpret_cast<const float*>(XL + (uint64_t)(uint32_t)iL[s] * ld_bytes));
+                    if (iR[s] >= 0) vR[s] = ldg4(reinterpret_cast<const float*>(XR + (uint64_t)(uint32_t)iR[s] * ld_bytes));
+                }
             }
         };
         uint32_t use = 0;          // chunks this group has fed so far
@@ -358,7 +405,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
 
         Cur k;
         k.w = blockIdx.x; k.titer = 0; k.c = 0; k.c1 = 0; k.row0 = 0; k.idx_a = 0; k.valid = false;
+        k.wlo = 0; k.wlen = 0; k.win_a = 0;
         enter(k, grp);
+        if (WIN) {
+            // shared-memory gathers complete in tens of cycles: one register set, gather -> feed -> next chunk; the
+            // window / index buffers are released (advance) only after feed() has consumed every loaded value
+            float4 aL[4], aR[4];
+            while (k.valid) {
+                gather(k, aL, aR);
+                feed(aL, aR);
+                advance(k);
+            }
+        } else {
         float4 aL[4], aR[4], bL[4], bR[4];
         if (k.valid) {
             gather(k, aL, aR);
@@ -374,6 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                 feed(bL, bR);
                 if (!more) break;
             }
+        }
         }
     } else if (warp == TC_WARP_LOAD) {
         // ===================== loader: weight images (one TMA bulk copy per chunk) and the
@@ -401,7 +460,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const TcParams p) {
                         }
                     }
                     const uint32_t bytes = (uint32_t)rows * 4u;
-                    mbar_arrive_expect_tx(&idx_full[b], bytes * (uint32_t)p.Ktaps);
+                    uint32_t wbytes = 0;
+                    int wlo = 0, wlen = 0;
+                    if (WIN) {
+                        wlo = __ldg(p.win + 2 * (w / ksplit));
+                        wlen = __ldg(p.win + 2 * (w / ksplit) + 1);
+                        wlen = wlen < p.win_cap ? wlen : p.win_cap;
+                        wbytes = (uint32_t)wlen * (uint32_t)p.ldx * 4u;
+                        s_wmeta[b * 2] = wlo;
+                        s_wmeta[b * 2 + 1] = wlen;
+                    }
+                    mbar_arrive_expect_tx(&idx_full[b], bytes * (uint32_t)p.Ktaps + wbytes);
+                    if (WIN && wbytes) {
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(s_win + (size_t)b * p.win_bytes)),
+                            "l"(p.X + (size_t)wlo * p.ldx), "r"(wbytes), "r"(smem_u32(&idx_full[b]))
+                            : "memory");
+                    }
                     for (int k = 0; k < p.Ktaps; ++k) {
                         asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -751,30 +827,30 @@ extern "C" int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy) 
 static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
                           long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K, const int* d_n_out,
                           int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats, float* wpack,
-                          int rows_hint, int prepacked, int* zero_sync, void* stream_);
+                          int rows_hint, int prepacked, int* zero_sync, const int* tile_win, void* stream_);
 
 extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
                               long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K,
                               const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
                               double* stats, float* wpack, int rows_hint, void* stream_) {
     return conv_tc_launch(X, ldx, Cin, W, w_sk, w_sci, w_sco, flip_k, nbr, tbl_stride, K, d_n_out, max_out, Y, ldy,
-                          Cout, accumulate, stats, wpack, rows_hint, 0, nullptr, stream_);
+                          Cout, accumulate, stats, wpack, rows_hint, 0, nullptr, nullptr, stream_);
 }
 
 // wpack already holds the weight image (gp_conv_tc_pack_batch); zero_sync (optional): two zero-initialised ints the
 // caller keeps for this stream - a split-K launch then clears its output rows itself instead of a k_zero_rows pass
 extern "C" int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride,
                               int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
-                              double* stats, int rows_hint, int* zero_sync, void* stream_) {
+                              double* stats, int rows_hint, int* zero_sync, const int* tile_win, void* stream_) {
     return conv_tc_launch(X, ldx, Cin, nullptr, 0, 0, 0, 0, nbr, tbl_stride, K, d_n_out, max_out, Y, ldy, Cout,
-                          accumulate, stats, const_cast<float*>(wpack), rows_hint, 1, zero_sync, stream_);
+                          accumulate, stats, const_cast<float*>(wpack), rows_hint, 1, zero_sync, tile_win, stream_);
 }
 
 static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long long w_sk,
                               long long w_sci, long long w_sco, int flip_k, const int* nbr, int tbl_stride,
                               int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout,
                               int accumulate, double* stats, float* wpack, int rows_hint, int prepacked,
-                              int* zero_sync, void* stream_) {
+                              int* zero_sync, const int* tile_win, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(gp_conv_tc_supported(Cin, Cout, K, ldx, ldy), "gp_conv_tc_fwd: unsupported shape Cin=%d Cout=%d K=%d",
                  Cin, Cout, K);
@@ -797,32 +873,56 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
         const char* tsp = getenv("GAPART_TC_TS");   // device pointer (decimal) of a [6*256] int64 trace buffer
         p.ts = tsp ? (long long*)strtoull(tsp, nullptr, 10) : nullptr;
     }
-    // Operand ring of TC_GROUPS * spg stages: a stage = 64 TMEM columns (A hi 32 | lo 32) + one weight image in
-    // shared memory.  Two stages per feeder group decouple the feeders from the MMA round trip (feed -> MMA ->
-    // commit -> free = 2-3 k cycles); wide accumulators / weight images trade the second accumulator buffer,
-    // then the second stage, for TMEM columns / shared memory.
-    p.accw = (Cout + 31) & ~31;
-    const size_t b_bytes = (size_t)Cout * 256;
-    const size_t fixed = 1024 /*align*/ + (size_t)2 * K * TC_ROWS * 4 + (size_t)2 * Cout * 8 + 512;
-    const size_t budget = 227 * 1024;
-    const bool smem2 = fixed + 2 * TC_GROUPS * b_bytes <= budget;
-    if (smem2 && 2 * p.accw + 2 * TC_GROUPS * 64 <= TC_TMEM_COLS) { p.nbuf = 2; p.spg = 2; }
-    else if (smem2 && p.accw + 2 * TC_GROUPS * 64 <= TC_TMEM_COLS) { p.nbuf = 1; p.spg = 2; }
-    else { p.nbuf = (2 * p.accw + TC_GROUPS * 64 <= TC_TMEM_COLS) ? 2 : 1; p.spg = 1; }
-    GP_CHECK_ARG(p.nbuf * p.accw + p.spg * TC_GROUPS * 64 <= TC_TMEM_COLS &&
-                     fixed + (size_t)p.spg * TC_GROUPS * b_bytes <= budget,
-                 "gp_conv_tc_fwd: Cout=%d exceeds tensor / shared memory", Cout);
-    p.inv_cin = (uint32_t)(0x100000000ull / (unsigned)Cin) + 1u;
-    size_t smem = fixed + (size_t)p.spg * TC_GROUPS * b_bytes;
-    static thread_local bool configured = false;
-    if (!configured) {
-        GP_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        configured = true;
-    }
     const int sms = gp_num_sms();
     const int ksplit = tc_ksplit(K, Cin, max_out, rows_hint);
     p.ksplit = ksplit;
     p.idx_bulk = (nbr != nullptr && (reinterpret_cast<size_t>(nbr) & 15) == 0 && (tbl_stride % 4) == 0) ? 1 : 0;
+    p.accw = (Cout + 31) & ~31;
+    const size_t b_bytes = (size_t)Cout * 256;
+    const size_t fixed = 1024 /*align*/ + (size_t)2 * K * TC_ROWS * 4 + (size_t)2 * Cout * 8 + 512;
+    const size_t budget = 227 * 1024;
+
+    // ---- shared-memory window variant: whole-tile work items (no split-K), dense rows (the window is ONE bulk copy),
+    // a per-tile window table, and room for two window buffers next to 3 x 2 operand stages ------------------------
+    static int win_enabled = -1;
+    if (win_enabled < 0) {
+        const char* e = getenv("GAPART_TC_WIN");
+        win_enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    bool use_win = win_enabled && tile_win != nullptr && ksplit == 1 && p.idx_bulk && ldx == Cin && K > 1;
+    int win_cap = 0;
+    if (use_win) {
+        const int G = 3;
+        const size_t row_b = (size_t)Cin * 4;
+        const bool tm_ok = 2 * p.accw + 2 * G * 64 <= TC_TMEM_COLS || p.accw + 2 * G * 64 <= TC_TMEM_COLS;
+        const size_t left = budget > fixed + 2 * G * b_bytes ? budget - fixed - 2 * G * b_bytes : 0;
+        win_cap = (int)((left / 2) / row_b);
+        win_cap &= ~7;
+        if (win_cap > 640) win_cap = 640;
+        if (!tm_ok || win_cap < 256) use_win = false;
+    }
+    const int G = use_win ? 3 : 2;
+    // Operand ring of G * spg stages: a stage = 64 TMEM columns (A hi 32 | lo 32) + one weight image in
+    // shared memory.  Two stages per feeder group decouple the feeders from the MMA round trip (feed -> MMA ->
+    // commit -> free = 2-3 k cycles); wide accumulators / weight images trade the second accumulator buffer,
+    // then the second stage, for TMEM columns / shared memory.
+    const bool smem2 = fixed + 2 * G * b_bytes <= budget;
+    if (smem2 && 2 * p.accw + 2 * G * 64 <= TC_TMEM_COLS) { p.nbuf = 2; p.spg = 2; }
+    else if (smem2 && p.accw + 2 * G * 64 <= TC_TMEM_COLS) { p.nbuf = 1; p.spg = 2; }
+    else { p.nbuf = (2 * p.accw + G * 64 <= TC_TMEM_COLS) ? 2 : 1; p.spg = 1; }
+    GP_CHECK_ARG(p.nbuf * p.accw + p.spg * G * 64 <= TC_TMEM_COLS && fixed + (size_t)p.spg * G * b_bytes <= budget,
+                 "gp_conv_tc_fwd: Cout=%d exceeds tensor / shared memory", Cout);
+    p.inv_cin = (uint32_t)(0x100000000ull / (unsigned)Cin) + 1u;
+    p.win = use_win ? tile_win : nullptr;
+    p.win_cap = win_cap;
+    p.win_bytes = use_win ? (int)(((size_t)win_cap * Cin * 4 + 127) & ~(size_t)127) : 0;
+    size_t smem = fixed + (size_t)p.spg * G * b_bytes + 2 * (size_t)p.win_bytes;
+    static thread_local bool configured = false;
+    if (!configured) {
+        GP_CUDA(cudaFuncSetAttribute(k_conv_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        GP_CUDA(cudaFuncSetAttribute(k_conv_tc<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        configured = true;
+    }
     int launches = prepacked ? 1 : 2;
     p.ns_feed = 32;
     p.ns_mma = 20;
@@ -845,9 +945,57 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
     }
     long long work = (long long)gp_cdiv(max_out, TC_ROWS) * ksplit;
     int grid = work < sms ? (int)work : sms;
-    GP_CUDA(gp_launch(k_conv_tc, dim3(grid), dim3(TC_THREADS), smem, stream, p));
+    if (use_win)
+        GP_CUDA(gp_launch(k_conv_tc<3, true>, dim3(grid), dim3(TC_THREADS_OF(3)), smem, stream, p));
+    else
+        GP_CUDA(gp_launch(k_conv_tc<2, false>, dim3(grid), dim3(TC_THREADS_OF(2)), smem, stream, p));
     gp_note_launch(launches);
     GP_LAUNCH_CHECK();
     if (ksplit > 1 && stats) return gp_col_stats(Y, ldy, Cout, d_n_out, max_out, stats, stream_);
+    return GP_OK;
+}
+
+// ---- per-tile row windows of a pair table ---------------------------------------------------------------------------
+// win[2 * t] = smallest valid neighbour row of tile t (128 consecutive output rows) over all taps, win[2 * t + 1] = number
+// of rows up to the largest one.  One warp per tile; the table of a level is shared by every conv (forward and input
+// gradient: tap k <-> K-1-k permutes the entries of a row, the SET of neighbours is the same) of the step.
+__global__ void __launch_bounds__(256) k_tile_windows(const int* __restrict__ nbr, int tbl_stride, int K,
+                                                      const int* __restrict__ d_n, int max_rows, int* __restrict__ win) {
+    gp_pdl_wait();
+    gp_pdl_trigger();
+    const int n = gp_rows(d_n, max_rows);
+    const int tile = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    const int n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
+    if (tile >= n_tiles) return;
+    const int r0 = tile * TC_ROWS;
+    int lo = 0x7fffffff, hi = -1;
+    for (int k = 0; k < K; ++k) {
+        const int* row = nbr + (size_t)k * tbl_stride + r0;
+#pragma unroll
+        for (int j = 0; j < TC_ROWS / 32; ++j) {
+            const int r = j * 32 + lane;
+            if (r0 + r < n) {
+                const int v = __ldg(row + r);
+                if (v >= 0) { lo = min(lo, v); hi = max(hi, v); }
+            }
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) {
+        win[2 * tile] = hi >= 0 ? lo : 0;
+        win[2 * tile + 1] = hi >= 0 ? hi - lo + 1 : 0;
+    }
+}
+
+extern "C" int gp_tile_windows(const int* nbr, int tbl_stride, int K, const int* d_n, int max_rows, int* tile_win,
+                               void* stream_) {
+    GP_CHECK_ARG(nbr != nullptr && tile_win != nullptr && K >= 1 && max_rows >= 0, "gp_tile_windows: bad arguments");
+    if (max_rows == 0) return GP_OK;
+    const int tiles = gp_cdiv(max_rows, TC_ROWS);
+    GP_CUDA(gp_launch(k_tile_windows, dim3(gp_cdiv((long long)tiles * 32, 256)), dim3(256), 0, (cudaStream_t)stream_, nbr,
+                      tbl_stride, K, d_n, max_rows, tile_win));
+    gp_note_launch(1);
+    GP_LAUNCH_CHECK();
     return GP_OK;
 }

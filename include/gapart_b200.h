@@ -139,11 +139,17 @@ int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w
  * out = gp_conv_tc_workspace_floats(K, Cin, Cout) floats, 16-byte aligned.
  * gp_conv_tc_run: gp_conv_tc_fwd on a packed image; zero_sync (optional): two zero-initialised ints owned by the
  * caller for this stream - split-K launches then clear their output rows in-kernel (grid counter) instead of a
- * separate zeroing launch; the kernel re-arms the counters before it exits. */
+ * separate zeroing launch; the kernel re-arms the counters before it exits.
 int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long total, void* stream);
+ * tile_win (optional, from gp_tile_windows on the same table): per 128-row tile the contiguous range of input rows that
+ * holds its neighbours; when given (and the launch is not K-split, rows are dense: ldx == Cin) the kernel stages that
+ * range in shared memory once per tile and gathers from there instead of fetching every (row, tap) pair from L2. */
 int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride, int K,
                    const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats,
-                   int rows_hint, int* zero_sync, void* stream);
+                   int rows_hint, int* zero_sync, const int* tile_win, void* stream);
+/* tile_win[2*t], tile_win[2*t+1] = first row / row count of the range spanned by the valid entries of rows
+ * [128 t, 128 t + 128) of a pair table nbr[K][tbl_stride]; tile_win holds 2 * ceil(max_rows / 128) ints. */
+int gp_tile_windows(const int* nbr, int tbl_stride, int K, const int* d_n, int max_rows, int* tile_win, void* stream);
 
 /* dW(k', ci, co) += sum_i X[nbr[k][i], ci] * dY[i, co] */
 int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout,
