@@ -252,8 +252,12 @@ static int ref_opt_n_threads(int work_size) {
 // round is: local arg-max -> warp shuffles -> one block barrier -> the CTA's candidate (distance, tie key, index, xyz)
 // is written into the shared memory of every CTA of the cluster (DSMEM) -> ONE cluster barrier -> every warp reduces
 // the cluster's candidates on its own.  The winner's coordinates travel with the candidate, so no global load sits on the
-// round's critical path.  Candidate slots are double buffered by round parity: a CTA can only overwrite a slot two
-// rounds later, i.e. after a cluster barrier that every reader of the slot has passed.
+// round's critical path.  The exchange is signalled through one mbarrier per CTA (every source CTA stores its
+// candidate into the destination's slot and arrives on the destination's barrier with release.cluster; the readers wait
+// with acquire.cluster on their LOCAL barrier) - the hardware cluster barrier over 8-16 x 1024 threads measured ~3 us
+// per round, this is a shared-memory poll.  Candidate slots are double buffered by round parity: a CTA can only
+// overwrite a slot two rounds later, and it gets there only after every CTA has arrived for the round in between,
+// which each CTA does after all its warps have read the slot.
 // The arg-max order (distance, bit-reversed reference slot, index) is total, so any reduction topology selects the
 // reference's winner: results stay bit-identical to sampling_gpu.cu:93-209 (tests/test_pointnet2_gpu.py).
 #include <cooperative_groups.h>
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, i
     __shared__ float s_d[32];
     __shared__ int s_key[32], s_k[32];
     __shared__ FpsCand s_cl[2][FPSC_CL];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int rank = (int)cluster.block_rank(), batch = blockIdx.x / FPSC_CL;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     dataset += (size_t)batch * n * 3;
@@ -293,6 +298,11 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, i
     }
     float x1 = dataset[0], y1 = dataset[1], z1 = dataset[2];      // the first sample is point 0
     if (rank == 0 && tid == 0) idxs[0] = 0;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(FPSC_CL));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     cluster.sync();
     for (int j = 1; j < m; ++j) {
         float best = -1.f;
@@ -342,9 +352,25 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, i
                 }
                 FpsCand* dst = cluster.map_shared_rank(&s_cl[par][rank], lane);
                 *dst = c;
+                uint32_t rbar;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar_a), "r"(lane));
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
             }
         }
-        cluster.sync();
+        {
+            // all FPSC_CL candidates of round j have landed in this CTA's slots
+            const uint32_t parity = (uint32_t)((j - 1) & 1);
+            uint32_t ok = 0;
+            while (true) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(bar_a), "r"(parity)
+                    : "memory");
+                if (ok) break;
+            }
+        }
         FpsCand c;
         c.d = -2.f; c.key = 0; c.k = 0; c.x = c.y = c.z = 0.f;
         if (lane < FPSC_CL) c = s_cl[par][lane];

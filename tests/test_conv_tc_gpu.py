@@ -199,3 +199,57 @@ def test_tc_index_tile_paths(cuda, cin, cout, pad):
     ops.conv_fwd(x, w, nbr, 27, M, d_n_out=d_n, out=y2, use_tc=True, rows_hint=n)
     assert rel_err(y2[:n], _ref(x, w, t["nbr"], 27, M)[:n]) < 6e-5
     assert float(y2[n:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cin,cout,shuffled", [(16, 16, False), (32, 32, False), (48, 48, False), (16, 32, True), (64, 64, False)])
+def test_tc_window_variant_matches(cuda, cin, cout, shuffled):
+    """shared-memory window variant (gp_tile_windows + tile_win argument, 3 feeder groups) == the global-gather variant
+    == fp64: rows in lexicographic order (neighbours inside the window), and rows in SHUFFLED order (ranges far longer
+    than the window buffer: most neighbours take the global fall-back), with the device-side row count short of the
+    bound and BatchNorm statistics from the epilogue."""
+    from gapartnet_b200._lib import C
+
+    t = _table(cuda, n=9000)
+    M = t["M"]
+    nbr = t["nbr"]
+    if shuffled:
+        g0 = torch.Generator().manual_seed(3)
+        perm = torch.randperm(M, generator=g0).to(cuda)                # new row r holds old row perm[r]
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(M, device=cuda)
+        old = nbr[:, perm].long()
+        nbr = torch.where(old >= 0, inv[old.clamp(min=0)], old).int().contiguous()
+    g = torch.Generator(device="cpu").manual_seed(cin * 77 + cout)
+    x = torch.randn(M + 64, cin, generator=g).to(cuda)
+    w = (torch.randn(cout, 27, cin, generator=g) * 0.1).to(cuda)
+    d_n = torch.tensor([M], dtype=torch.int32, device=cuda)
+    bound = M + 64
+    tbl = torch.full((27, bound), -1, dtype=torch.int32, device=cuda)
+    tbl[:, :M] = nbr
+    win = torch.zeros(2 * ((bound + 127) // 128), dtype=torch.int32, device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    C.gp_tile_windows(tbl.data_ptr(), bound, 27, d_n.data_ptr(), bound, win.data_ptr(), st)
+    # windows really bracket every neighbour
+    wv = win.view(-1, 2).cpu().numpy()
+    nb = tbl[:, :M].cpu().numpy()
+    for tile in range((M + 127) // 128):
+        blk = nb[:, tile * 128:(tile + 1) * 128]
+        v = blk[blk >= 0]
+        assert wv[tile, 0] == v.min() and wv[tile, 0] + wv[tile, 1] - 1 == v.max()
+    ws = torch.empty(int(C.gp_conv_tc_workspace_floats(27, cin, cout)), device=cuda)
+    ys = []
+    for use_win in (False, True):
+        y = torch.full((bound, cout), 7.0, device=cuda)
+        stats = torch.zeros(2 * cout, dtype=torch.float64, device=cuda)
+        if not ys:   # first call packs the weights
+            C.gp_conv_tc_fwd(x.data_ptr(), cin, cin, w.data_ptr(), cin, 1, 27 * cin, 0, tbl.data_ptr(), bound, 27,
+                             d_n.data_ptr(), bound, y.data_ptr(), cout, cout, 0, None, ws.data_ptr(), M, st)
+        C.gp_conv_tc_run(x.data_ptr(), cin, cin, ws.data_ptr(), tbl.data_ptr(), bound, 27, d_n.data_ptr(), bound,
+                         y.data_ptr(), cout, cout, 0, stats.data_ptr(), M, None, win.data_ptr() if use_win else None, st)
+        torch.cuda.synchronize()
+        assert bool((y[M:] == 7.0).all())                  # rows beyond the device count are untouched
+        ys.append((y[:M].clone(), stats.clone()))
+    ref = _ref(x[:M], w, tbl[:, :M], 27, M)
+    assert rel_err(ys[1][0], ref) < 6e-5
+    assert torch.equal(ys[0][0], ys[1][0])                 # same MMAs in the same order: bit-identical
+    assert rel_err(ys[1][1][:cout], ref.sum(0)) < 1e-4 and rel_err(ys[1][1][cout:], ref.square().sum(0)) < 1e-4
