@@ -582,6 +582,59 @@ extern "C" int gp_instance_iou(const int* proposal_offsets, const int* instance_
 }
 
 // ---------------------------------------------------------------------------------------------
+// proposal-vs-proposal point-set IoU (apply_nms, grouping_utils.py:229-243: csr @ csr.t() -> dense P x P -> IoU).
+// A point joins at most one proposal per clustering, so a row of the membership matrix has at most TWO entries and
+// the sparse product degenerates to: diag = proposal size, off-diagonal (a, b) += 1 for every point that is in both.
+// memb: int2 per point (the two proposal ids or -1); d_err |= 1 if a point shows up in three or more proposals
+// (not a GAPartNet proposal set: the caller falls back / raises).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_piou_members(const int* __restrict__ offsets, const int* __restrict__ point_of, int P, int num_points,
+                               int* __restrict__ memb, int* __restrict__ d_err) {
+    const int p = blockIdx.x;
+    const int b = offsets[p], e = offsets[p + 1];
+    for (int t = b + threadIdx.x; t < e; t += blockDim.x) {
+        const int j = point_of[t];
+        if (j < 0 || j >= num_points) { atomicOr(d_err, 2); continue; }
+        if (atomicCAS(memb + 2 * j, -1, p) != -1) {
+            if (atomicCAS(memb + 2 * j + 1, -1, p) != -1) atomicOr(d_err, 1);
+        }
+    }
+}
+__global__ void k_piou_count(const int* __restrict__ memb, int num_points, int P, float* __restrict__ inter) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= num_points) return;
+    const int a = memb[2 * j], b = memb[2 * j + 1];
+    if (a >= 0 && b >= 0 && a != b) {
+        atomicAdd(inter + (size_t)a * P + b, 1.0f);
+        atomicAdd(inter + (size_t)b * P + a, 1.0f);
+    }
+}
+__global__ void k_piou_finish(const int* __restrict__ offsets, int P, float* __restrict__ ious) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P * P) return;
+    const int a = (int)(t / P), b = (int)(t - (long long)a * P);
+    const float na = (float)(offsets[a + 1] - offsets[a]), nb = (float)(offsets[b + 1] - offsets[b]);
+    const float inter = a == b ? na : ious[t];
+    // ious = intersection / (union + 1e-8), union = n_a + n_b - intersection (fp32, the reference's operation order)
+    ious[t] = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(na, nb), inter), 1e-8f));
+}
+
+extern "C" int gp_proposal_iou(const int* proposal_offsets, const int* point_of, int P, int num_points, int* memb_ws,
+                               float* ious, int* d_err, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_CHECK_ARG(P >= 0 && num_points >= 0 && (long long)P * P < (1ll << 31), "gp_proposal_iou: bad sizes");
+    if (P == 0) return GP_OK;
+    GP_CUDA(cudaMemsetAsync(memb_ws, 0xff, (size_t)2 * (num_points > 0 ? num_points : 1) * sizeof(int), stream));
+    GP_CUDA(cudaMemsetAsync(ious, 0, (size_t)P * P * sizeof(float), stream));
+    k_piou_members<<<P, 128, 0, stream>>>(proposal_offsets, point_of, P, num_points, memb_ws, d_err);
+    if (num_points > 0) k_piou_count<<<gp_cdiv(num_points, 256), 256, 0, stream>>>(memb_ws, num_points, P, ious);
+    k_piou_finish<<<gp_cdiv((long long)P * P, 256), 256, 0, stream>>>(proposal_offsets, P, ious);
+    gp_note_launch(3);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // greedy NMS on a dense IoU matrix; `order` = proposal ids by descending score
 // keep[i] = 1 if order[i] survives; single CTA (P is a few hundred proposals)
 // ---------------------------------------------------------------------------------------------

@@ -74,14 +74,69 @@ def get_gt_scores(ious: torch.Tensor, fg_thresh: float = 0.75, bg_thresh: float 
     return scores
 
 
-def proposal_nms(proposal_offsets, sorted_indices, num_points: int, scores, threshold: float):
-    """point-set IoU between proposals (sparse membership product, grouping_utils.py:234-243) + greedy NMS"""
+def proposal_iou(proposal_offsets, sorted_indices, num_points: int) -> torch.Tensor:
+    """[P,P] point-set IoU between proposals (the csr @ csr.t() of apply_nms, grouping_utils.py:229-243) on the GPU:
+    one pass over the proposal points, no sparse-sparse product"""
+    from .._lib import C, GapartError
+    from ..ops import _p, _stream
+
+    if not sorted_indices.is_cuda:
+        raise GapartError("proposal_iou needs CUDA tensors (no CPU fallback)")
     P = proposal_offsets.numel() - 1
-    counts = (proposal_offsets[1:] - proposal_offsets[:-1]).float()
-    rows = torch.repeat_interleave(torch.arange(P, device=scores.device), counts.long())
-    m = torch.sparse_coo_tensor(torch.stack([rows, sorted_indices.long()]),
-                                torch.ones(rows.numel(), dtype=torch.float32, device=scores.device),
-                                size=(P, num_points)).coalesce()
-    inter = torch.sparse.mm(m, m.t()).to_dense()
-    ious = inter / (counts[:, None] + counts[None, :] - inter)
-    return nms(ious, scores, threshold)
+    dev = sorted_indices.device
+    off = proposal_offsets.to(torch.int32).contiguous()
+    pt = sorted_indices.to(torch.int32).contiguous()
+    ious = torch.empty(P, P, dtype=torch.float32, device=dev)
+    memb = torch.empty(2 * max(num_points, 1), dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    C.gp_proposal_iou(_p(off), _p(pt), P, int(num_points), _p(memb), _p(ious), _p(err), _stream())
+    e = int(err.item())
+    if e:
+        raise GapartError("proposal_iou: a point belongs to more than two proposals" if e & 1 else
+                          "proposal_iou: point index out of range")
+    return ious
+
+
+_PER_POINT = ("sorted_indices", "pt_xyz", "batch_indices", "sem_preds", "sem_labels", "instance_labels", "npcs_valid_mask")
+_PER_PROPOSAL = ("score_preds", "ious")
+
+
+def _select_proposals(proposals: dict, valid_proposals_mask: torch.Tensor) -> dict:
+    """keep the proposals of a mask and re-compact ids / CSR offsets: the common second half of
+    filter_invalid_proposals (grouping_utils.py:171-218) and apply_nms (:246-298)"""
+    pidx = proposals["proposal_indices"]
+    valid_points = valid_proposals_mask[pidx]
+    _, new_idx, n_per = torch.unique_consecutive(pidx[valid_points], return_inverse=True, return_counts=True)
+    off = torch.zeros(n_per.shape[0] + 1, dtype=torch.int32, device=pidx.device)
+    off[1:] = n_per.cumsum(0)
+    out = dict(proposals)
+    out.update(proposal_offsets=off, proposal_indices=new_idx, num_points_per_proposal=n_per)
+    for k in _PER_POINT:
+        if proposals.get(k) is not None:
+            out[k] = proposals[k][valid_points]
+    for k in _PER_PROPOSAL:
+        if proposals.get(k) is not None:
+            out[k] = proposals[k][valid_proposals_mask]
+    nv = proposals.get("npcs_valid_mask")
+    vn = valid_points[nv] if nv is not None else valid_points
+    for k in ("npcs_preds", "gt_npcs"):
+        if proposals.get(k) is not None:
+            out[k] = proposals[k][vn]
+    return out
+
+
+def filter_invalid_proposals(proposals: dict, score_threshold: float, min_num_points_per_proposal: int) -> dict:
+    """grouping_utils.py:159-218: drop proposals with score <= threshold or too few points"""
+    keep = (proposals["score_preds"] > score_threshold) & (proposals["num_points_per_proposal"] > min_num_points_per_proposal)
+    return _select_proposals(proposals, keep)
+
+
+def apply_nms(proposals: dict, iou_threshold: float = 0.3) -> dict:
+    """grouping_utils.py:221-298: point-set IoU between proposals -> greedy NMS by descending score"""
+    num_points = int(proposals["valid_mask"].sum()) if proposals.get("valid_mask") is not None \
+        else int(proposals["sorted_indices"].max()) + 1
+    ious = proposal_iou(proposals["proposal_offsets"], proposals["sorted_indices"], num_points)
+    keep = nms(ious, proposals["score_preds"], iou_threshold)
+    mask = torch.zeros(ious.shape[0], dtype=torch.bool, device=ious.device)
+    mask[keep] = True
+    return _select_proposals(proposals, mask)

@@ -140,10 +140,10 @@ int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w
  * gp_conv_tc_run: gp_conv_tc_fwd on a packed image; zero_sync (optional): two zero-initialised ints owned by the
  * caller for this stream - split-K launches then clear their output rows in-kernel (grid counter) instead of a
  * separate zeroing launch; the kernel re-arms the counters before it exits.
-int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long total, void* stream);
  * tile_win (optional, from gp_tile_windows on the same table): per 128-row tile the contiguous range of input rows that
  * holds its neighbours; when given (and the launch is not K-split, rows are dense: ldx == Cin) the kernel stages that
  * range in shared memory once per tile and gathers from there instead of fetching every (row, tap) pair from L2. */
+int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long total, void* stream);
 int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride, int K,
                    const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats,
                    int rows_hint, int* zero_sync, const int* tile_win, void* stream);
@@ -260,6 +260,14 @@ int gp_segmented_reduce(const float* x, int ldx, int C, const int* begin, const 
  * num_points_per_instance) -> ious [P, Imax] (gapartnet/network/model.py:373-378) */
 int gp_instance_iou(const int* proposal_offsets, const int* instance_labels, const int* batch_indices,
                     const int* num_points_per_instance, int P, int Imax, float* ious, void* stream);
+
+/* apply_nms' pairwise proposal IoU (gapartnet/network/grouping_utils.py:229-243: sparse membership matrix csr @ csr.t()
+ * -> dense [P,P] intersections -> intersection / (n_a + n_b - intersection + 1e-8)).  proposal_offsets int32 [P+1] (CSR),
+ * point_of[t] = point id in [0, num_points) of proposal point t.  A point may belong to at most two proposals (one per
+ * clustering, which is what GAPartNet produces): *d_err |= 1 otherwise, |= 2 on a point id out of range.
+ * memb_ws: 2 * num_points ints of scratch; ious [P,P] fp32 out. */
+int gp_proposal_iou(const int* proposal_offsets, const int* point_of, int P, int num_points, int* memb_ws, float* ious,
+                    int* d_err, void* stream);
 
 /* epic_ops.nms.nms(ious [P,P], scores, threshold) (gapartnet/network/grouping_utils.py:244): greedy;
  * order = proposal ids by descending score (caller sorts), keep[i] = 1 iff order[i] survives. */

@@ -148,6 +148,25 @@ def main():
         num_points_per_instance=proposals.num_points_per_instance.numpy(),
         level0_voxels=int(pcs[0].voxel_coords.shape[0] + pcs[1].voxel_coords.shape[0]),
     )
+    # validation tail of the reference (model.py:676-682): filter_invalid_proposals -> apply_nms on this step's proposals.
+    # apply_nms moves the IoU matrix with .cuda() (grouping_utils.py:244); on this CPU-only box that call is an identity.
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        pf = ref_gu.filter_invalid_proposals(proposals, score_threshold=0.3, min_num_points_per_proposal=8)
+        pn = ref_gu.apply_nms(pf, 0.3)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    for tag, pr in (("val_filter", pf), ("val_nms", pn)):
+        out[tag + "/proposal_offsets"] = pr.proposal_offsets.numpy()
+        out[tag + "/sorted_indices"] = pr.sorted_indices.numpy()
+        out[tag + "/proposal_indices"] = pr.proposal_indices.numpy()
+        out[tag + "/score_preds"] = pr.score_preds.numpy()
+        out[tag + "/sem_preds"] = pr.sem_preds.numpy()
+        out[tag + "/batch_indices"] = pr.batch_indices.numpy()
+        out[tag + "/ious"] = pr.ious.numpy()
+    print("validation tail: %d proposals -> filter %d -> nms %d" % (
+        proposals.proposal_offsets.shape[0] - 1, pf.proposal_offsets.shape[0] - 1, pn.proposal_offsets.shape[0] - 1))
     for k, n in names.items():
         out[k] = float(logged[n])
     for k, g, p in zip(GRAD_KEYS, g_prop, gp):

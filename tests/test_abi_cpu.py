@@ -19,6 +19,18 @@ def test_library_exports_all_symbols():
     assert lib.gp_version() >= 1
 
 
+def test_every_exported_entry_point_is_declared():
+    """the other direction: every gp_* symbol the library exports has a prototype in the header (a prototype swallowed by
+    a comment block would otherwise only surface as a KeyError on the GPU box)"""
+    import subprocess
+
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("gp_") and " T " in ln}
+    declared = set(_lib.symbols())
+    internal = {s for s in exported if s in ("gp_set_error",)}
+    assert exported - declared - internal == set(), sorted(exported - declared - internal)
+
+
 def test_signatures_are_plain_c():
     """no torch / C++ types across the boundary: only pointers, ints, floats"""
     for name, (ret, ptypes) in _lib.parse_header().items():

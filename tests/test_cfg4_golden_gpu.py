@@ -133,3 +133,43 @@ def test_segmented_voxelize_stage_is_bit_exact(cuda, gold):
     vf, vc, pcid = segmented_voxelize(xyz, feats, off, pidx, n_per, 28, 50, rand=torch.from_numpy(g["rand"]).to(cuda))
     np.testing.assert_array_equal(vc.cpu().numpy(), g["voxel_coords"])
     np.testing.assert_array_equal(pcid.cpu().numpy(), g["pc_voxel_id"])
+
+
+def test_validation_tail_matches_the_reference(cuda, gold):
+    """filter_invalid_proposals + apply_nms (model.py:676-682, grouping_utils.py:159-298) on the GPU - point-set IoU by
+    the membership kernel gp_proposal_iou instead of csr @ csr.t(), greedy NMS by gp_nms - against the reference's own
+    functions run on the same step (fixture keys val_filter/*, val_nms/*).  The scores are taken from the fixture so that
+    the threshold decisions do not hinge on the last bits of a sigmoid."""
+    from gapartnet_b200.network.grouping_utils import apply_nms, filter_invalid_proposals, proposal_iou
+
+    g, cfg = gold
+    net, batch = _model(cuda, cfg)
+    with torch.no_grad():
+        out = net.training_step(batch, training_schedule=(0, 0), rand=torch.from_numpy(g["rand"]).to(cuda))
+    p = out["proposals"]
+    np.testing.assert_array_equal(p["sorted_indices"].cpu().numpy(), g["sorted_indices"])
+    p["score_preds"] = torch.from_numpy(g["score_preds"]).to(cuda)
+    pf = filter_invalid_proposals(p, score_threshold=0.3, min_num_points_per_proposal=8)
+    pn = apply_nms(pf, 0.3)
+    for tag, pr in (("val_filter", pf), ("val_nms", pn)):
+        np.testing.assert_array_equal(pr["proposal_offsets"].cpu().numpy(), g[tag + "/proposal_offsets"])
+        np.testing.assert_array_equal(pr["sorted_indices"].cpu().numpy(), g[tag + "/sorted_indices"])
+        np.testing.assert_array_equal(pr["proposal_indices"].cpu().numpy(), g[tag + "/proposal_indices"])
+        np.testing.assert_array_equal(pr["sem_preds"].cpu().numpy(), g[tag + "/sem_preds"])
+        np.testing.assert_array_equal(pr["batch_indices"].cpu().numpy(), g[tag + "/batch_indices"])
+        np.testing.assert_array_equal(pr["score_preds"].cpu().numpy(), g[tag + "/score_preds"])
+        np.testing.assert_array_equal(pr["ious"].cpu().numpy(), g[tag + "/ious"])
+    assert 0 < pn["proposal_offsets"].numel() < pf["proposal_offsets"].numel() < p["proposal_offsets"].numel()
+    # the IoU matrix itself against the dense definition
+    off = pf["proposal_offsets"].cpu().numpy()
+    idx = pf["sorted_indices"].cpu().numpy()
+    P = off.shape[0] - 1
+    nv = int(g["valid_mask"].sum())
+    memb = np.zeros((P, nv), np.float32)
+    for a in range(P):
+        memb[a, idx[off[a]:off[a + 1]]] = 1
+    inter = memb @ memb.T
+    n = memb.sum(1)
+    ref = inter / (n[:, None] + n[None, :] - inter + np.float32(1e-8))
+    got = proposal_iou(pf["proposal_offsets"], pf["sorted_indices"], nv).cpu().numpy()
+    np.testing.assert_array_equal(got, ref.astype(np.float32))
