@@ -88,6 +88,26 @@ int gp_voxelize(const float* xyz, int xyz_stride, const float* feats, int C, int
 int gp_count_dropped(const int* pc_voxel_id, const int64_t* batch_offsets, int batch, int N, int* d_count,
                      void* stream);
 
+/* ---- in-step data path (GAPartNetDataset.__getitem__, gapartnet/dataset/gapartnet.py:66-82, on the device) ---------- */
+/* apply_augmentations (:85-120): xyz <- xyz @ M[scene] (mats: device double [batch,3,3], row-major, the reference's m),
+ * features 3..3+n_color += color[scene] (device double [batch,n_color] or NULL); fp64 arithmetic, rounded once, as numpy
+ * does for float32 @ float64.  The random draws that build M / color stay on the host (same RNG consumption). */
+int gp_augment_points(float* points, int stride, const int64_t* batch_offsets, int batch, int N, const double* mats,
+                      const double* color, int n_color, void* stream);
+/* compact_instance_labels (:134-143): per scene the labels >= 0 are renumbered 0..k-1 in ascending order of the old
+ * label (np.unique(return_inverse)), in place; d_num_instances[batch] = k.  Labels must be < max_label (*d_err |= 1).
+ * ws: batch * (max_label + 1) ints. */
+int gp_compact_instance_labels(int* labels, const int64_t* batch_offsets, int batch, int N, int max_label, int* ws,
+                               int* d_num_instances, int* d_err, void* stream);
+/* generate_inst_info (:145-176) + the padding of PointCloud.collate (structure/point_cloud.py:112-121): for every
+ * instance (label in [0, Imax)) of every scene the mean / min / max of its points' xyz, written to regions [N,9] of each
+ * of its points (0 elsewhere); num_points_per_instance [batch,Imax] (0 padded); instance_sem_labels [batch,Imax] =
+ * sem_labels of the instance's first point (-1 padded).  ws: gp_instance_info_ws_bytes(batch, Imax) bytes, 8-aligned. */
+long long gp_instance_info_ws_bytes(int batch, int Imax);
+int gp_instance_info(const float* xyz, int stride, const int* labels, const int64_t* sem_labels,
+                     const int64_t* batch_offsets, int batch, int N, int Imax, void* ws, float* regions,
+                     int* num_points_per_instance, int* instance_sem_labels, void* stream);
+
 /* ---- rulebooks (indice pairs) ---------------------------------------------------------------- */
 /* SubMConv3d(kernel_size=3, padding=1, indice_key=...) pair table
  * (gapartnet/network/backbone.py:25-28,33-36,149-152):
