@@ -263,7 +263,19 @@ static int ref_opt_n_threads(int work_size) {
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-struct FpsCand { float d; int key; int k; float x, y, z; };
+// A candidate is ordered by (distance, reference tie key, index).  Packed for the reductions: hi = bits(d) + 1 (d >= 0,
+// so the float bits are monotone; 0 is reserved for "idle thread", which the reference initialises to (-1, point 0) and
+// which therefore loses against every real candidate), lo = ~((key << 17) | k) (key < 1024, k < 2^17: smaller key, then
+// smaller index wins).  A warp arg-max is then TWO redux instructions instead of 15 shuffles + compare chains - with
+// 1024 threads per CTA the shuffle reductions, not the distance updates, were the bulk of a round (3.1 us).
+struct FpsCand { unsigned hi, lo; float x, y, z; };
+
+__device__ __forceinline__ void fps_warp_max(unsigned& hi, unsigned& lo) {
+    const unsigned h = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned l = __reduce_max_sync(0xffffffffu, hi == h ? lo : 0u);
+    hi = h;
+    lo = l;
+}
 
 template <int PPT, int FPSC_CL>
 __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, int bs_ref,
@@ -272,8 +284,7 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, i
     if (m <= 0) return;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ float s_xyz[];                 // [PPT * FPS_THREADS][3] this CTA's coordinates (winner lookup)
-    __shared__ float s_d[32];
-    __shared__ int s_key[32], s_k[32];
+    __shared__ unsigned s_hi[32], s_lo[32];
     __shared__ FpsCand s_cl[2][FPSC_CL];
     __shared__ __align__(8) unsigned long long s_bar;
     const int rank = (int)cluster.block_rank(), batch = blockIdx.x / FPSC_CL;
@@ -304,9 +315,9 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, i
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster.sync();
+    const unsigned idle_lo = ~0u;                    // (key 0, point 0)
     for (int j = 1; j < m; ++j) {
-        float best = -1.f;
-        int bk = 0, bkey = 0;
+        unsigned bhi = 0u, blo = idle_lo;
 #pragma unroll
         for (int u = 0; u < PPT; ++u) {
             const int k = base + u * FPS_THREADS + tid;
@@ -315,40 +326,28 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, i
                 float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
                 float d2 = min(d, pt[u]);
                 pt[u] = d2;
-                int key = fps_key(k, bs_ref);
-                if (fps_better(d2, key, k, best, bkey, bk)) { best = d2; bk = k; bkey = key; }
+                const unsigned hi = __float_as_uint(d2) + 1u;
+                const unsigned lo = ~(((unsigned)fps_key(k, bs_ref) << 17) | (unsigned)k);
+                if (hi > bhi || (hi == bhi && lo > blo)) { bhi = hi; blo = lo; }
             }
         }
-        // the reference starts every thread at (best=-1, besti=0): an idle thread contributes point 0
-        if (best < 0.f) { bk = 0; bkey = 0; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float od = __shfl_xor_sync(0xffffffffu, best, o);
-            int okey = __shfl_xor_sync(0xffffffffu, bkey, o);
-            int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (fps_better(od, okey, ok, best, bkey, bk)) { best = od; bkey = okey; bk = ok; }
-        }
-        if (lane == 0) { s_d[wid] = best; s_key[wid] = bkey; s_k[wid] = bk; }
+        fps_warp_max(bhi, blo);
+        if (lane == 0) { s_hi[wid] = bhi; s_lo[wid] = blo; }
         __syncthreads();
         const int par = j & 1;
         if (wid == 0) {
-            best = s_d[lane]; bkey = s_key[lane]; bk = s_k[lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                float od = __shfl_xor_sync(0xffffffffu, best, o);
-                int okey = __shfl_xor_sync(0xffffffffu, bkey, o);
-                int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                if (fps_better(od, okey, ok, best, bkey, bk)) { best = od; bkey = okey; bk = ok; }
-            }
+            bhi = s_hi[lane]; blo = s_lo[lane];
+            fps_warp_max(bhi, blo);
             // every lane holds the CTA's winner; lane r publishes it to CTA r of the cluster
             if (lane < FPSC_CL) {
                 FpsCand c;
-                c.d = best; c.key = bkey; c.k = bk;
+                c.hi = bhi; c.lo = blo;
+                const int bk = (int)(~blo & 0x1ffffu);
                 const int loc = bk - base;
-                if (loc >= 0 && loc < PPT * FPS_THREADS) {
+                if (bhi != 0u && loc >= 0 && loc < PPT * FPS_THREADS) {
                     c.x = s_xyz[(size_t)loc * 3]; c.y = s_xyz[(size_t)loc * 3 + 1]; c.z = s_xyz[(size_t)loc * 3 + 2];
-                } else {          // an all-idle CTA contributes point 0 (never wins against a real candidate with d >= 0
-                    c.x = dataset[0]; c.y = dataset[1]; c.z = dataset[2];   // unless it ties at (d, key 0, k 0) = itself)
+                } else {          // an all-idle CTA contributes point 0, which only wins if every CTA is idle
+                    c.x = dataset[0]; c.y = dataset[1]; c.z = dataset[2];
                 }
                 FpsCand* dst = cluster.map_shared_rank(&s_cl[par][rank], lane);
                 *dst = c;
@@ -372,23 +371,16 @@ __global__ void __launch_bounds__(FPS_THREADS) k_pn2_fps_cluster(int n, int m, i
             }
         }
         FpsCand c;
-        c.d = -2.f; c.key = 0; c.k = 0; c.x = c.y = c.z = 0.f;
+        c.hi = 0u; c.lo = 0u; c.x = c.y = c.z = 0.f;
         if (lane < FPSC_CL) c = s_cl[par][lane];
-        int src = lane;
-#pragma unroll
-        for (int o = FPSC_CL / 2; o > 0; o >>= 1) {
-            float od = __shfl_xor_sync(0xffffffffu, c.d, o);
-            int okey = __shfl_xor_sync(0xffffffffu, c.key, o);
-            int ok = __shfl_xor_sync(0xffffffffu, c.k, o);
-            int osrc = __shfl_xor_sync(0xffffffffu, src, o);
-            if (fps_better(od, okey, ok, c.d, c.key, c.k)) { c.d = od; c.key = okey; c.k = ok; src = osrc; }
-        }
-        const int win = __shfl_sync(0xffffffffu, src, 0);
-        const int old = __shfl_sync(0xffffffffu, c.k, 0);
+        unsigned whi = c.hi, wlo = c.lo;
+        fps_warp_max(whi, wlo);
+        const unsigned who = __ballot_sync(0xffffffffu, lane < FPSC_CL && c.hi == whi && c.lo == wlo);
+        const int win = __ffs(who) - 1;
         x1 = __shfl_sync(0xffffffffu, c.x, win);
         y1 = __shfl_sync(0xffffffffu, c.y, win);
         z1 = __shfl_sync(0xffffffffu, c.z, win);
-        if (rank == 0 && tid == 0) idxs[j] = old;
+        if (rank == 0 && tid == 0) idxs[j] = (int)(~wlo & 0x1ffffu);
     }
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {
