@@ -251,18 +251,21 @@ __global__ void k_cg_fill(const int* __restrict__ keys, int n, const int* __rest
     int c = atomicAdd(counts + key, -1);        // counts down to 0: slot c-1 of the cell
     order[starts[key] + c - 1] = i;
 }
-#define CG_ROUNDS 16                        // candidate rounds a warp keeps in registers (16 x 32 = 512 candidates)
+#define CG_HSLOTS 16                        // a warp keeps up to 16 x 32 = 512 HITS of its query in registers
+#define CG_WARPS 8                          // warps (queries) per CTA
 
 // One WARP per query (queries taken in cell order).  The 27 cells of a query are 9 contiguous runs of the cell-sorted
 // point list (one per (x, y) column); the warp flattens them into one candidate sequence and tests 32 candidates per
-// round with coalesced loads of `order`.  Each lane keeps the hits of its rounds in registers.
+// round with coalesced loads of `order`.  Hits are compacted through a per-warp shared-memory strip (ballot + popc
+// prefix) and read back into registers, slot s of lane l = hit number 32 s + l.
 // The reference semantics are "the first `cap` hits in ascending point index" (a linear scan that stops at the cap); the
 // edges only depend on that SET, so a truncated query bisects the index threshold T = cap-th smallest hit index with
-// warp-wide counts (registers + one reduction per step) and unions the hits <= T.  History: the r1 kernel fell back to an
-// O(N/B) ordered scan for truncated queries (42 ms per call when an untrained semantic head predicts one class
-// everywhere); a thread-per-query version with the hit list in local memory still spent 3 ms per call on the bisection's
-// local-memory traffic.  More than CG_ROUNDS*32 candidates (very dense scenes): the same algorithm re-tests the
-// candidates in every bisection step instead of keeping them.
+// warp-wide counts (registers + one redux per step) and unions the hits <= T.
+// History (profiles/r2_summary.md): the r1 kernel fell back to an O(N/B) ordered scan for truncated queries (42 ms per
+// call when an untrained semantic head predicts one class everywhere); thread-per-query with the hit list in local
+// memory: 3 ms (the bisection's local-memory traffic); warp-per-query keeping CANDIDATES (not hits) in registers: 14 ms,
+// because ball-normalised scenes put 300-600 points into the 27 cells and every query overflowed into re-scanning.
+// More than 512 hits (very dense scenes): the bisection re-tests the candidates instead.
 struct CgRuns {
     int pre[10];   // prefix of the 9 run lengths (uniform)
     int jb[9];     // run starts
@@ -290,13 +293,15 @@ __device__ __forceinline__ bool cg_hit(const float4* __restrict__ pts, int k, co
     return d2 < radius2;
 }
 
-__global__ void __launch_bounds__(256) k_cg_cluster(const float4* __restrict__ pts, const int* __restrict__ batch_indices,
-                                                    const int* __restrict__ batch_offsets, int Q,
-                                                    const int* __restrict__ d_n, float radius2, int cap,
-                                                    int use_labels, const unsigned* __restrict__ mn, float inv_cell,
-                                                    const int* __restrict__ starts, const int* __restrict__ order,
-                                                    int* __restrict__ num, int* __restrict__ parent) {
+__global__ void __launch_bounds__(32 * CG_WARPS) k_cg_cluster(const float4* __restrict__ pts, const int* __restrict__ batch_indices,
+                                                              const int* __restrict__ batch_offsets, int Q,
+                                                              const int* __restrict__ d_n, float radius2, int cap,
+                                                              int use_labels, const unsigned* __restrict__ mn, float inv_cell,
+                                                              const int* __restrict__ starts, const int* __restrict__ order,
+                                                              int* __restrict__ num, int* __restrict__ parent) {
+    __shared__ int s_hits[CG_WARPS][CG_HSLOTS * 32];
     const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    int* strip = s_hits[threadIdx.x >> 5];
     Q = gp_rows(d_n, Q);
     if (t >= Q) return;
     const int q = __ldg(order + t);
@@ -325,25 +330,32 @@ __global__ void __launch_bounds__(256) k_cg_cluster(const float4* __restrict__ p
     }
     r.pre[9] = run;
     const int total = run;
-    const bool fits = total <= CG_ROUNDS * 32;
 
-    int hits[CG_ROUNDS];
+    // ---- one pass over the candidates: hits compacted into the warp's strip ---------------------------------------------
     int tot = 0;
-    if (fits) {
-#pragma unroll
-        for (int rd = 0; rd < CG_ROUNDS; ++rd) {
-            hits[rd] = -1;
-            const int u = rd * 32 + lane;
-            if (u < total) {
-                const int k = cg_candidate(r, u, order);
-                if (cg_hit(pts, k, c, lab, use_labels, radius2)) { hits[rd] = k; ++tot; }
-            }
+    for (int u0 = 0; u0 < total; u0 += 32) {
+        const int u = u0 + lane;
+        int k = -1;
+        bool hit = false;
+        if (u < total) {
+            k = cg_candidate(r, u, order);
+            hit = cg_hit(pts, k, c, lab, use_labels, radius2);
         }
-    } else {
-        for (int u = lane; u < total; u += 32)
-            tot += cg_hit(pts, cg_candidate(r, u, order), c, lab, use_labels, radius2) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int h = tot + __popc(bal & ((1u << lane) - 1u));
+            if (h < CG_HSLOTS * 32) strip[h] = k;
+        }
+        tot += __popc(bal);
     }
-    tot = __reduce_add_sync(0xffffffffu, tot);
+    const bool fits = tot <= CG_HSLOTS * 32;
+    __syncwarp();
+    int hits[CG_HSLOTS];
+#pragma unroll
+    for (int sl = 0; sl < CG_HSLOTS; ++sl) {
+        const int h = sl * 32 + lane;
+        hits[sl] = (fits && h < tot) ? strip[h] : -1;
+    }
 
     int T = 0x7fffffff;      // union every hit with index <= T
     if (tot > cap) {
@@ -353,7 +365,7 @@ __global__ void __launch_bounds__(256) k_cg_cluster(const float4* __restrict__ p
             int cnt = 0;
             if (fits) {
 #pragma unroll
-                for (int rd = 0; rd < CG_ROUNDS; ++rd) cnt += (hits[rd] >= 0 && hits[rd] <= mid) ? 1 : 0;
+                for (int sl = 0; sl < CG_HSLOTS; ++sl) cnt += (hits[sl] >= 0 && hits[sl] <= mid) ? 1 : 0;
             } else {
                 for (int u = lane; u < total; u += 32) {
                     const int k = cg_candidate(r, u, order);
@@ -366,22 +378,21 @@ __global__ void __launch_bounds__(256) k_cg_cluster(const float4* __restrict__ p
         T = lo;
         tot = cap;
     }
-    // Warp-aggregated unions: all lanes link INTO the same vertex q, so naive per-lane uf_union(q, k) calls fight over
-    // parent[root(q)] (one compare-and-swap wins, 31 lanes retry with fresh finds: measured 15 ms per call).  Per round
-    // every lane finds the root of its own hit, the warp agrees on the smallest root m among them and root(q), and each
-    // lane hooks ITS root under m - distinct addresses, no retries in the common case.
+    // Warp-aggregated unions: all lanes link INTO the same vertex q; per round every lane finds the root of its own hit,
+    // the warp agrees on the smallest root m among them and root(q), and each lane hooks ITS root under m - distinct
+    // addresses, no compare-and-swap fights over parent[root(q)].
     auto union_round = [&](int k, bool has) {
         const int rq = uf_find(parent, q);
-        const int r = has ? uf_find(parent, k) : 0x7fffffff;
-        const int m = min(rq, __reduce_min_sync(0xffffffffu, r));
-        if (has && r != m) uf_union(parent, m, r);
+        const int rk = has ? uf_find(parent, k) : 0x7fffffff;
+        const int m = min(rq, __reduce_min_sync(0xffffffffu, rk));
+        if (has && rk != m) uf_union(parent, m, rk);
         if (lane == 0 && rq != m) uf_union(parent, m, rq);
     };
     if (fits) {
 #pragma unroll
-        for (int rd = 0; rd < CG_ROUNDS; ++rd) {
-            const bool has = hits[rd] >= 0 && hits[rd] <= T && hits[rd] != q;
-            if (__any_sync(0xffffffffu, has)) union_round(hits[rd], has);
+        for (int sl = 0; sl < CG_HSLOTS; ++sl) {
+            const bool has = hits[sl] >= 0 && hits[sl] <= T && hits[sl] != q;
+            if (__any_sync(0xffffffffu, has)) union_round(hits[sl], has);
         }
     } else {
         for (int u0 = 0; u0 < total; u0 += 32) {
@@ -436,7 +447,7 @@ int cg_cluster_packed(const float4* pts4, const int* batch_indices, const int* b
     k_cg_count<<<g, 256, 0, stream>>>(pts4, batch_indices, N, d_n, mn, inv_cell, keys, counts);
     GP_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, temp, counts, starts, (int)(cells + 1), stream));
     k_cg_fill<<<g, 256, 0, stream>>>(keys, N, d_n, starts, counts, order);
-    k_cg_cluster<<<gp_cdiv((long long)N * 32, 256), 256, 0, stream>>>(pts4, batch_indices, batch_offsets, N, d_n,
+    k_cg_cluster<<<gp_cdiv((long long)N, CG_WARPS), 32 * CG_WARPS, 0, stream>>>(pts4, batch_indices, batch_offsets, N, d_n,
                                                                       radius * radius, num_samples, use_labels, mn,
                                                                       inv_cell, starts, order, num_points_per_query,
                                                                       cc_labels);

@@ -51,6 +51,9 @@
 
 // trace slot = sequence number of the chunk within CTA 0 (quadrant-1 warp of every feeder group + the MMA warp)
 #define TC_TS(ev, g) do { if (p.ts && blockIdx.x == 0 && lane == 0 && (g) < 256) p.ts[(ev) * 256 + (g)] = clock64(); } while (0)
+// trace events [8][256]: 0 feed enter, 1 stage free seen, 2 MMA warp: accumulator buffer free (first chunk of a tile),
+// 3 fed (A in TMEM, arrived), 4 MMA issue begins, 5 MMA issue done + commit, 6 loader: weight copy of the chunk issued,
+// 7 epilogue: tile stored (indexed by the chunk sequence number of the tile's first chunk)
 
 // K position `col` (0..31) of a chunk's TMEM operand holds source float tc_kperm(col) of the chunk:
 // tcgen05.st.16x256b puts registers {4n+2h+e} of thread (g, q) at lane g+8h, column 8n+2q+e; a feeder thread
@@ -153,6 +156,12 @@ struct TcParams {
     // shared-memory window variant (WIN): win[2 * tile] = first row, win[2 * tile + 1] = row count of the contiguous
     // row range of X that holds (nearly) all neighbours of the tile; win_bytes = bytes of one window buffer
     const int* win; int win_cap; int win_bytes;
+    // wide-N (Cout <= 32): the hi and lo weight images of a chunk are adjacent row blocks of ONE K-major tile, so
+    // [W_hi | W_lo] is a single B operand with N = 2*Cout.  Per K step two MMAs (A_hi x [W_hi|W_lo], A_lo x [W_hi|W_lo])
+    // replace three; the accumulator holds D1 = hi*hi + lo*hi and D2 = hi*lo + lo*lo side by side and the epilogue adds
+    // them.  The issuing thread needs ~37 cycles per tcgen05.mma whatever its size (clock64 trace), while an N = 16 MMA
+    // occupies the tensor pipe for 18: fewer, wider MMAs are the lever at the levels that hold 84 % of the work.
+    int wide;
 };
 
 __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const float* v) {
@@ -440,6 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
         int stage = 0;
         uint32_t ph = 0;
         int titer = 0;
+        int lseq = 0;      // chunk sequence number (trace only)
         // index tile of work item w (the t-th of this CTA) into buffer t&1.  Its previous user (work item
         // t-2) must have released it; `try_only` polls instead of blocking so that the weight pipeline of the
         // current work item is never held up by the prefetch.  Returns true once issued.
@@ -512,6 +522,8 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
                     for (int c = c0; c < c1; ++c) {
                         if (pending && solo) pending = !load_idx_tile(w_next, titer + 1, true);
                         mbar_wait(&st_free[stage], ph ^ 1);
+                        if (p.ts && blockIdx.x == 0 && lseq < 256) p.ts[6 * 256 + lseq] = clock64();
+                        ++lseq;
                         mbar_arrive_expect_tx(&st_full[stage], b_bytes);
                         const float* src = p.Wpack + (size_t)c * Cout * 64;
                         asm volatile(
@@ -533,8 +545,9 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
         // ===================== MMA issuer =====================
         // every operand below is warp-uniform (made explicit with shfl) so the elected lane issues
         // UTCHMMA straight from uniform registers
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Cout >> 3) << 17) |
-                               ((uint32_t)(TC_ROWS >> 4) << 24);
+        const uint32_t n_mma = p.wide ? 2u * (uint32_t)Cout : (uint32_t)Cout;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_mma >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        const bool wide = p.wide != 0;
         const uint32_t tbase = uniform(tmem_base);
         const uint32_t tiles_u32 = uniform(smem_u32(tiles));
         const uint32_t free_u32 = uniform(smem_u32(st_free));
@@ -548,6 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
             const int part = w % ksplit;
             const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
             mbar_wait_warp(&acc_empty[buf], acc_ph ^ 1, lane);
+            TC_TS(2, seqn);
             // operands of the first chunk; inside the loop the wait for chunk c+1 is issued between the MMAs
             // of chunk c so that its ~100-cycle latency overlaps the tensor pipe draining its queue (a tf32
             // MMA of M=128, K=8 occupies the pipe for 10 + N/2 cycles: tools/micro/mma_rate.cu)
@@ -579,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
                         }
                         tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, (c > c0 || ks > 0) ? 1u : 0u);
                         tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
-                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_lo, idesc, 1u);
+                        if (!wide) tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_lo, idesc, 1u);
                     }
                     // TMEM A stage and weight stage are reusable once these retire
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -617,6 +631,7 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
         }
         bool zero_seen = p.zero_sync == nullptr;
         int buf = 0;
+        int eseq = 0;      // chunk sequence number of the current tile's first chunk (trace only)
         uint32_t acc_ph = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int tile = w / ksplit;
@@ -650,10 +665,23 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
                       "=r"(v[15])
                     : "r"(taddr + (uint32_t)c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float f[16];
+                if (p.wide) {
+                    uint32_t v2[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+                          "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]),
+                          "=r"(v2[15])
+                        : "r"(taddr + (uint32_t)(Cout + c0)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < 16; ++e) f[e] = active ? __uint_as_float(v[e]) : 0.f;
+                    for (int e = 0; e < 16; ++e) f[e] = active ? __uint_as_float(v[e]) + __uint_as_float(v2[e]) : 0.f;
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = active ? __uint_as_float(v[e]) : 0.f;
+                }
                 if (active && ksplit > 1) {
                     // partial tile of a split GEMM-K axis: fp32 reductions into the (pre-zeroed or
                     // accumulated-into) output rows
@@ -733,6 +761,11 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (warp == 1) TC_TS(7, eseq);
+            {
+                const int part_e = w % ksplit;
+                eseq += ((part_e + 1) * p.n_chunks) / ksplit - (part_e * p.n_chunks) / ksplit;
+            }
             if (++buf == nbuf) {
                 buf = 0;
                 acc_ph ^= 1;
@@ -877,7 +910,13 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
     const int ksplit = tc_ksplit(K, Cin, max_out, rows_hint);
     p.ksplit = ksplit;
     p.idx_bulk = (nbr != nullptr && (reinterpret_cast<size_t>(nbr) & 15) == 0 && (tbl_stride % 4) == 0) ? 1 : 0;
-    p.accw = (Cout + 31) & ~31;
+    static int wide_enabled = -1;
+    if (wide_enabled < 0) {
+        const char* e = getenv("GAPART_TC_WIDE");
+        wide_enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.wide = (wide_enabled && Cout <= 32) ? 1 : 0;
+    p.accw = ((p.wide ? 2 * Cout : Cout) + 31) & ~31;
     const size_t b_bytes = (size_t)Cout * 256;
     const size_t fixed = 1024 /*align*/ + (size_t)2 * K * TC_ROWS * 4 + (size_t)2 * Cout * 8 + 512;
     const size_t budget = 227 * 1024;

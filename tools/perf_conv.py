@@ -47,14 +47,14 @@ for (cin, cout, rows) in [(16, 16, M), (32, 32, M // 3), (64, 64, M // 36), (112
 # timestamp trace of CTA 0 (last tile of the CTA is what remains in the buffer)
 CT = int(os.environ.get("TRACE_C", "16"))
 ROWS = int(os.environ.get("TRACE_ROWS", str(M)))
-ts = torch.zeros(6 * 256, dtype=torch.int64, device=dev)
+ts = torch.zeros(8 * 256, dtype=torch.int64, device=dev)
 os.environ["GAPART_TC_TS"] = str(ts.data_ptr())
 x = torch.randn(M, CT, device=dev); w = torch.randn(CT, 27, CT, device=dev) * 0.1
 d_n = torch.tensor([ROWS], dtype=torch.int32, device=dev); y = torch.empty(M, CT, device=dev)
 for _ in range(3):
     ops.conv_fwd(x, w, nbr, 27, M, d_n_out=d_n, out=y, use_tc=True)
 torch.cuda.synchronize()
-t = ts.cpu().numpy().reshape(6, 256)
+t = ts.cpu().numpy().reshape(8, 256)
 nch = (27 * CT + 31) // 32
 t0 = t[0, 0]
 names = ["feed", "free", "x", "fed", "mma0", "mma1"]
