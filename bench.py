@@ -349,7 +349,7 @@ def run_ours(args):
 
         t_conv = time_launch(lambda: C.gp_conv_tc_run(
             x.data_ptr(), 16, 16, ws.data_ptr(), nbr.data_ptr(), nbr.shape[1], 27, dn.data_ptr(), eng.max_rows[0],
-            y.data_ptr(), 16, 16, 0, None, M0, 0, eng.win[0].data_ptr(), st))
+            y.data_ptr(), 16, 16, 0, None, M0, 0, eng.win[0].data_ptr(), eng.tile_tbl[0].data_ptr(), st))
         t_wgrad = time_launch(lambda: C.gp_conv_wgrad_tc(
             x.data_ptr(), 16, 16, dyv.data_ptr(), 16, 16, nbr.data_ptr(), nbr.shape[1], 27, dn.data_ptr(),
             eng.max_rows[0], dw.data_ptr(), 16, 1, 27 * 16, M0, st))

@@ -156,6 +156,7 @@ struct TcParams {
     // shared-memory window variant (WIN): win[2 * tile] = first row, win[2 * tile + 1] = row count of the contiguous
     // row range of X that holds (nearly) all neighbours of the tile; win_bytes = bytes of one window buffer
     const int* win; int win_cap; int win_bytes;
+    const int* tile_tbl;   // optional tile-major copy of the table, [tile][Ktaps][128] (gp_tile_windows): one bulk copy per tile
     // wide-N (Cout <= 32): the hi and lo weight images of a chunk are adjacent row blocks of ONE K-major tile, so
     // [W_hi | W_lo] is a single B operand with N = 2*Cout.  Per K step two MMAs (A_hi x [W_hi|W_lo], A_lo x [W_hi|W_lo])
     // replace three; the accumulator holds D1 = hi*hi + lo*hi and D2 = hi*lo + lo*lo side by side and the epilogue adds
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
     uint64_t* idx_empty = idx_full + 2;           // [2]   every feeder warp is done with the index tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(idx_empty + 2);
     int* s_wmeta = reinterpret_cast<int*>(tmem_slot + 2);     // [2][2] first row / row count of the window buffers
+    float* s_zero = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_wmeta + 4) + 15) & ~(uintptr_t)15);   // 16 B of zeros
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ksplit = p.ksplit;
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 2 * Cout; i += TC_THREADS) s_stats[i] = 0.0;
+    if (tid < 4) s_zero[tid] = 0.f;
     if (warp == TC_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)TC_TMEM_COLS));
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
             enter(k, over);
         };
         const bool ragged_k = (p.Ktaps * p.Cin) % TC_KCHUNK != 0;   // last chunk reaches past the last tap
+        const uint32_t zero_a = smem_u32(s_zero);
         auto gather = [&](const Cur& k, float4* vL, float4* vR) {
             // K position of the thread's left / right piece: kk = tap*Cin + ci
             const uint32_t kkL = (uint32_t)k.c * TC_KCHUNK + 4u * q, kkR = kkL + 16u;
@@ -349,20 +353,27 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
                 }
             }
             if (WIN) {
-                const uint32_t oL = (uint32_t)(XL - Xb), oR = (uint32_t)(XR - Xb);
+                // branch-free: all 8 shared-memory loads issue back to back (a branch per piece serialised them: the
+                // trace showed ~1400 cycles per gather); an absent neighbour reads a 16-byte zero block, a neighbour
+                // beyond the window buffer (idx - wlo wraps to a huge value for idx = -1 as well) takes the rare
+                // global fall-back after a warp vote
+                const uint32_t oL = k.win_a + (uint32_t)(XL - Xb), oR = k.win_a + (uint32_t)(XR - Xb);
+                bool far = false;
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    vL[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    vR[s] = vL[s];
-                    if (iL[s] >= 0) {
-                        const uint32_t loc = (uint32_t)(iL[s] - k.wlo);
-                        vL[s] = loc < (uint32_t)k.wlen ? lds_f32x4(k.win_a + loc * ld_bytes + oL)
-                                                       : ldg4(reinterpret_cast<const float*>(XL + (uint64_t)(uint32_t)iL[s] * ld_bytes));
-                    }
-                    if (iR[s] >= 0) {
-                        const uint32_t loc = (uint32_t)(iR[s] - k.wlo);
-                        vR[s] = loc < (uint32_t)k.wlen ? lds_f32x4(k.win_a + loc * ld_bytes + oR)
-                                                       : ldg4(reinterpret_cast<const float*>(XR + (uint64_t)(uint32_t)iR[s] * ld_bytes));
+                    const uint32_t locL = (uint32_t)(iL[s] - k.wlo), locR = (uint32_t)(iR[s] - k.wlo);
+                    const bool inL = locL < (uint32_t)k.wlen, inR = locR < (uint32_t)k.wlen;
+                    vL[s] = lds_f32x4(inL ? oL + locL * ld_bytes : zero_a);
+                    vR[s] = lds_f32x4(inR ? oR + locR * ld_bytes : zero_a);
+                    far |= (!inL && iL[s] >= 0) || (!inR && iR[s] >= 0);
+                }
+                if (__any_sync(0xffffffffu, far)) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        if (iL[s] >= 0 && (uint32_t)(iL[s] - k.wlo) >= (uint32_t)k.wlen)
+                            vL[s] = ldg4(reinterpret_cast<const float*>(XL + (uint64_t)(uint32_t)iL[s] * ld_bytes));
+                        if (iR[s] >= 0 && (uint32_t)(iR[s] - k.wlo) >= (uint32_t)k.wlen)
+                            vR[s] = ldg4(reinterpret_cast<const float*>(XR + (uint64_t)(uint32_t)iR[s] * ld_bytes));
                     }
                 }
             } else {
@@ -444,23 +455,27 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
         }
         }
     } else if (warp == TC_WARP_LOAD) {
-        // ===================== loader: weight images (one TMA bulk copy per chunk) and the
-        // neighbour-index tile of the NEXT work item (Ktaps bulk copies of 512 B) =====================
-        int stage = 0;
-        uint32_t ph = 0;
-        int titer = 0;
-        int lseq = 0;      // chunk sequence number (trace only)
-        // index tile of work item w (the t-th of this CTA) into buffer t&1.  Its previous user (work item
-        // t-2) must have released it; `try_only` polls instead of blocking so that the weight pipeline of the
-        // current work item is never held up by the prefetch.  Returns true once issued.
-        auto load_idx_tile = [&](int w, int t, bool try_only) -> bool {
-            const int b = t & 1;
-            int* dst = s_idx + b * n_idx;
-            const int row0 = (w / ksplit) * TC_ROWS;
-            int rows = p.tbl_stride - row0;
-            rows = rows < TC_ROWS ? rows : TC_ROWS;
-            if (p.idx_bulk) {
-                if (lane == 0) {   // only lane 0 runs the loader in this mode
+        // ===================== loader: weight images (one TMA bulk copy per chunk) and the neighbour-index tile
+        // (+ row window) of the NEXT work item =====================
+        const bool solo = p.idx_bulk || !use_tbl;
+        if (solo) {
+            // ONE elected thread (elect.sync, not `lane == 0`: the copies then issue straight from uniform registers;
+            // behind a lane test ptxas wraps every UBLKCP in an R2UR waterfall loop - ~180 cycles per copy measured).
+            if (elect_one()) {
+                int stage = 0;
+                uint32_t ph = 0;
+                int titer = 0;
+                int lseq = 0;      // chunk sequence number (trace only)
+                // index tile (+ window) of work item w (the t-th of this CTA) into buffer t & 1.  Its previous user
+                // (work item t-2) must have released it; `try_only` polls instead of blocking so that the weight
+                // pipeline of the current work item is never held up by the prefetch.  Returns true once issued.
+                auto load_idx_tile = [&](int w, int t, bool try_only) -> bool {
+                    const int b = t & 1;
+                    int* dst = s_idx + b * n_idx;
+                    const int tile = w / ksplit;
+                    const int row0 = tile * TC_ROWS;
+                    int rows = p.tbl_stride - row0;
+                    rows = rows < TC_ROWS ? rows : TC_ROWS;
                     if (t >= 2) {
                         const uint32_t par = ((t >> 1) & 1) ^ 1;
                         if (try_only) {
@@ -471,56 +486,48 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
                     }
                     const uint32_t bytes = (uint32_t)rows * 4u;
                     uint32_t wbytes = 0;
-                    int wlo = 0, wlen = 0;
                     if (WIN) {
-                        wlo = __ldg(p.win + 2 * (w / ksplit));
-                        wlen = __ldg(p.win + 2 * (w / ksplit) + 1);
+                        const int wlo = __ldg(p.win + 2 * tile);
+                        int wlen = __ldg(p.win + 2 * tile + 1);
                         wlen = wlen < p.win_cap ? wlen : p.win_cap;
                         wbytes = (uint32_t)wlen * (uint32_t)p.ldx * 4u;
                         s_wmeta[b * 2] = wlo;
                         s_wmeta[b * 2 + 1] = wlen;
+                        if (wbytes) {
+                            mbar_arrive_expect_tx(&idx_full[b], (p.tile_tbl ? (uint32_t)n_idx * 4u : bytes * (uint32_t)p.Ktaps) + wbytes);
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                    smem_u32(s_win + (size_t)b * p.win_bytes)),
+                                "l"(p.X + (size_t)wlo * p.ldx), "r"(wbytes), "r"(smem_u32(&idx_full[b]))
+                                : "memory");
+                        }
                     }
-                    mbar_arrive_expect_tx(&idx_full[b], bytes * (uint32_t)p.Ktaps + wbytes);
-                    if (WIN && wbytes) {
+                    if (!wbytes) mbar_arrive_expect_tx(&idx_full[b], p.tile_tbl ? (uint32_t)n_idx * 4u : bytes * (uint32_t)p.Ktaps);
+                    if (p.tile_tbl) {
+                        // tile-major copy of the table (gp_tile_windows): the whole [Ktaps][128] tile is ONE bulk copy
                         asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                smem_u32(s_win + (size_t)b * p.win_bytes)),
-                            "l"(p.X + (size_t)wlo * p.ldx), "r"(wbytes), "r"(smem_u32(&idx_full[b]))
+                                smem_u32(dst)),
+                            "l"(p.tile_tbl + (size_t)tile * n_idx), "r"((uint32_t)n_idx * 4u), "r"(smem_u32(&idx_full[b]))
                             : "memory");
+                    } else {
+                        for (int k = 0; k < p.Ktaps; ++k) {
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                    smem_u32(dst + k * TC_ROWS)),
+                                "l"(p.nbr + (size_t)k * p.tbl_stride + row0), "r"(bytes), "r"(smem_u32(&idx_full[b]))
+                                : "memory");
+                        }
                     }
-                    for (int k = 0; k < p.Ktaps; ++k) {
-                        asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                smem_u32(dst + k * TC_ROWS)),
-                            "l"(p.nbr + (size_t)k * p.tbl_stride + row0), "r"(bytes), "r"(smem_u32(&idx_full[b]))
-                            : "memory");
-                    }
-                }
-                return true;
-            }
-            // unaligned table (compat path): plain loads by the whole warp, blocking
-            if (try_only) return false;
-            if (t >= 2) mbar_wait_warp(&idx_empty[b], ((t >> 1) & 1) ^ 1, lane);
-            for (int e = lane; e < n_idx; e += 32) {
-                const int k = e >> 7, r = e & 127;
-                dst[e] = r < rows ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row0 + r) : -1;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&idx_full[b]);
-            __syncwarp();
-            return true;
-        };
-        const bool solo = p.idx_bulk || !use_tbl;   // lane 0 alone runs the whole loader loop
-        if (!solo || lane == 0) {
-            if (use_tbl && (int)blockIdx.x < n_work) load_idx_tile(blockIdx.x, 0, false);
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++titer) {
-                const int w_next = w + (int)gridDim.x;
-                bool pending = use_tbl && w_next < n_work;
-                const int part = w % ksplit;
-                const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
-                if (lane == 0) {
+                    return true;
+                };
+                if (use_tbl && (int)blockIdx.x < n_work) load_idx_tile(blockIdx.x, 0, false);
+                for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++titer) {
+                    const int w_next = w + (int)gridDim.x;
+                    bool pending = use_tbl && w_next < n_work;
+                    const int part = w % ksplit;
+                    const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
                     for (int c = c0; c < c1; ++c) {
-                        if (pending && solo) pending = !load_idx_tile(w_next, titer + 1, true);
                         mbar_wait(&st_free[stage], ph ^ 1);
                         if (p.ts && blockIdx.x == 0 && lseq < 256) p.ts[6 * 256 + lseq] = clock64();
                         ++lseq;
@@ -535,84 +542,119 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
                             stage = 0;
                             ph ^= 1;
                         }
+                        // the prefetch of the next work item's indices comes AFTER this chunk's weights: it is needed a
+                        // whole tile later, the weights now
+                        if (pending) pending = !load_idx_tile(w_next, titer + 1, true);
+                    }
+                    if (pending) load_idx_tile(w_next, titer + 1, false);
+                }
+            }
+            __syncwarp();
+        } else {
+            // unaligned table (compat path): the whole warp fetches the index tile with plain loads, blocking
+            int stage = 0;
+            uint32_t ph = 0;
+            int titer = 0;
+            auto load_idx_tile = [&](int w, int t) {
+                const int b = t & 1;
+                int* dst = s_idx + b * n_idx;
+                const int row0 = (w / ksplit) * TC_ROWS;
+                int rows = p.tbl_stride - row0;
+                rows = rows < TC_ROWS ? rows : TC_ROWS;
+                if (t >= 2) mbar_wait_warp(&idx_empty[b], ((t >> 1) & 1) ^ 1, lane);
+                for (int e = lane; e < n_idx; e += 32) {
+                    const int k = e >> 7, r = e & 127;
+                    dst[e] = r < rows ? __ldg(p.nbr + (size_t)k * p.tbl_stride + row0 + r) : -1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&idx_full[b]);
+                __syncwarp();
+            };
+            if ((int)blockIdx.x < n_work) load_idx_tile(blockIdx.x, 0);
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++titer) {
+                const int w_next = w + (int)gridDim.x;
+                const int part = w % ksplit;
+                const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
+                if (lane == 0) {
+                    for (int c = c0; c < c1; ++c) {
+                        mbar_wait(&st_free[stage], ph ^ 1);
+                        mbar_arrive_expect_tx(&st_full[stage], b_bytes);
+                        const float* src = p.Wpack + (size_t)c * Cout * 64;
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(tiles + (size_t)stage * b_bytes)),
+                            "l"(src), "r"(b_bytes), "r"(smem_u32(&st_full[stage]))
+                            : "memory");
+                        if (++stage == SB) {
+                            stage = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
-                if (!solo) __syncwarp();
-                if (pending) load_idx_tile(w_next, titer + 1, false);
+                __syncwarp();
+                if (w_next < n_work) load_idx_tile(w_next, titer + 1);
             }
         }
     } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer =====================
-        // every operand below is warp-uniform (made explicit with shfl) so the elected lane issues
-        // UTCHMMA straight from uniform registers
-        const uint32_t n_mma = p.wide ? 2u * (uint32_t)Cout : (uint32_t)Cout;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_mma >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-        const bool wide = p.wide != 0;
-        const uint32_t tbase = uniform(tmem_base);
-        const uint32_t tiles_u32 = uniform(smem_u32(tiles));
-        const uint32_t free_u32 = uniform(smem_u32(st_free));
-        // descriptor high word is constant: SBO = 1024 B, version 1, SWIZZLE_128B
-        const uint32_t desc_hi = (uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
-        int sa = 0, seqn = 0;
-        uint32_t pa = 0;
-        int buf = 0;
-        uint32_t acc_ph = 0;             // parity of the current use of accumulator buffer `buf`
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int part = w % ksplit;
-            const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
-            mbar_wait_warp(&acc_empty[buf], acc_ph ^ 1, lane);
-            TC_TS(2, seqn);
-            // operands of the first chunk; inside the loop the wait for chunk c+1 is issued between the MMAs
-            // of chunk c so that its ~100-cycle latency overlaps the tensor pipe draining its queue (a tf32
-            // MMA of M=128, K=8 occupies the pipe for 10 + N/2 cycles: tools/micro/mma_rate.cu)
-            mbar_wait_warp(&st_full[sa], pa, lane);
-            tc_fence_after();
-            const uint32_t d_tmem = tbase + (uint32_t)buf * accw;
-            for (int c = c0; c < c1; ++c) {
-                TC_TS(4, seqn);
-                const uint32_t b_hi = tiles_u32 + (uint32_t)sa * b_bytes;
-                const uint32_t b_lo = b_hi + (uint32_t)Cout * 128;
-                const uint32_t a_hi = tbase + a_base + (uint32_t)sa * 64;
-                const uint32_t free_bar = free_u32 + (uint32_t)sa * 8;
-                int sn = sa + 1;
-                uint32_t pn = pa;
-                if (sn == SA) {
-                    sn = 0;
-                    pn ^= 1;
-                }
-                const uint32_t next_bar = uniform(smem_u32(&st_full[sn]));
-                const bool more = c + 1 < c1;
-                if (elect_one()) {
+        // ONE elected thread runs the whole role.  The tensor pipe takes a tf32 MMA of M = 128, K = 8 every 10 + N/2
+        // cycles and its queue is shallow (the issuing thread is throttled to that rate, tools/micro/mma_rate.cu), so
+        // every instruction this thread spends between two MMAs is tensor-pipe idle time: a clock64 trace of the
+        // previous warp-wide loop (shuffles, elect, syncwarp, R2UR chains per chunk) showed 650-800 cycles per chunk of
+        // which 210 were tensor pipe.  Hence: no warp-level operations inside the loop, running stage counters, one
+        // blocking wait per chunk.
+        if (elect_one()) {
+            const uint32_t n_mma = p.wide ? 2u * (uint32_t)Cout : (uint32_t)Cout;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_mma >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+            const bool wide = p.wide != 0;
+            // descriptor high word is constant: SBO = 1024 B, version 1, SWIZZLE_128B
+            const uint64_t desc_hi = (uint64_t)((uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29)) << 32;
+            const uint32_t tiles16 = smem_u32(tiles) >> 4, b16 = b_bytes >> 4, lo16 = (uint32_t)Cout * 8u;
+            const uint32_t free0 = smem_u32(st_free), full0 = smem_u32(st_full);
+            const uint32_t a0 = tmem_base + a_base;
+            uint32_t sa = 0, pa = 0, seqn = 0;
+            int buf = 0;
+            uint32_t acc_ph = 0;             // parity of the current use of accumulator buffer `buf`
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int part = w % ksplit;
+                const int c0 = (part * p.n_chunks) / ksplit, c1 = ((part + 1) * p.n_chunks) / ksplit;
+                mbar_wait(&acc_empty[buf], acc_ph ^ 1);
+                if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[2 * 256 + seqn] = clock64();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * accw;
+                uint32_t acc = 0;
+                for (int c = c0; c < c1; ++c) {
+                    mbar_wait_addr_sleep(full0 + sa * 8u, pa, (uint32_t)p.ns_mma);
+                    tc_fence_after();
+                    if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[4 * 256 + seqn] = clock64();
+                    const uint32_t a_hi = a0 + sa * 64u;
+                    const uint32_t bd = tiles16 + sa * b16;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_hi + ks * 32) >> 4) & 0x3FFF);
-                        const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_lo + ks * 32) >> 4) & 0x3FFF);
-                        if (ks == 3 && more) {
-                            mbar_wait_sleep(&st_full[sn], pn, (uint32_t)p.ns_mma);
-                            tc_fence_after();
-                        }
-                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, (c > c0 || ks > 0) ? 1u : 0u);
+                        const uint64_t db_hi = desc_hi | (uint64_t)(bd + ks * 2);
+                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, ks == 0 ? acc : 1u);
                         tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
-                        if (!wide) tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_lo, idesc, 1u);
+                        if (!wide) tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, desc_hi | (uint64_t)(bd + lo16 + ks * 2), idesc, 1u);
                     }
+                    acc = 1u;
                     // TMEM A stage and weight stage are reusable once these retire
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     free_bar)
+                                     free0 + sa * 8u)
                                  : "memory");
+                    if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[5 * 256 + seqn] = clock64();
+                    ++seqn;
+                    if (++sa == (uint32_t)SA) {
+                        sa = 0;
+                        pa ^= 1;
+                    }
                 }
-                __syncwarp();
-                TC_TS(5, seqn);
-                ++seqn;
-                sa = sn;
-                pa = pn;
-            }
-            if (elect_one()) tc_commit(&acc_full[buf]);
-            __syncwarp();
-            if (++buf == nbuf) {
-                buf = 0;
-                acc_ph ^= 1;
+                tc_commit(&acc_full[buf]);
+                if (++buf == nbuf) {
+                    buf = 0;
+                    acc_ph ^= 1;
+                }
             }
         }
+        __syncwarp();
     } else {
         // ===================== epilogue (warps 0-3) =====================
         if (p.zero_sync) {
@@ -857,33 +899,40 @@ extern "C" int gp_conv_tc_supported(int Cin, int Cout, int K, int ldx, int ldy) 
            (ldx % 4 == 0) && (ldy % 4 == 0) && (long long)K * Cin + 32 < 65536;
 }
 
+// conv_win.cu: the specialised shared-memory window kernel (whole tiles, K = 27, Cin in {16, 32, 48, 64})
+int conv_win_launch(const float* X, int Cin, const float* wpack, const int* tile_tbl, const int* tile_win, const int* d_n_out,
+                    int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats, int n_chunks, long long* ts,
+                    int ns_feed, int ns_mma, cudaStream_t stream);
+
 static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
                           long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K, const int* d_n_out,
                           int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats, float* wpack,
-                          int rows_hint, int prepacked, int* zero_sync, const int* tile_win, void* stream_);
+                          int rows_hint, int prepacked, int* zero_sync, const int* tile_win, const int* tile_tbl,
+                          void* stream_);
 
 extern "C" int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w_sk, long long w_sci,
                               long long w_sco, int flip_k, const int* nbr, int tbl_stride, int K,
                               const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
                               double* stats, float* wpack, int rows_hint, void* stream_) {
     return conv_tc_launch(X, ldx, Cin, W, w_sk, w_sci, w_sco, flip_k, nbr, tbl_stride, K, d_n_out, max_out, Y, ldy,
-                          Cout, accumulate, stats, wpack, rows_hint, 0, nullptr, nullptr, stream_);
+                          Cout, accumulate, stats, wpack, rows_hint, 0, nullptr, nullptr, nullptr, stream_);
 }
 
 // wpack already holds the weight image (gp_conv_tc_pack_batch); zero_sync (optional): two zero-initialised ints the
 // caller keeps for this stream - a split-K launch then clears its output rows itself instead of a k_zero_rows pass
 extern "C" int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride,
                               int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate,
-                              double* stats, int rows_hint, int* zero_sync, const int* tile_win, void* stream_) {
+                              double* stats, int rows_hint, int* zero_sync, const int* tile_win, const int* tile_tbl,
+                              void* stream_) {
     return conv_tc_launch(X, ldx, Cin, nullptr, 0, 0, 0, 0, nbr, tbl_stride, K, d_n_out, max_out, Y, ldy, Cout,
-                          accumulate, stats, const_cast<float*>(wpack), rows_hint, 1, zero_sync, tile_win, stream_);
+                          accumulate, stats, const_cast<float*>(wpack), rows_hint, 1, zero_sync, tile_win, tile_tbl, stream_);
 }
 
 static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long long w_sk,
                               long long w_sci, long long w_sco, int flip_k, const int* nbr, int tbl_stride,
                               int K, const int* d_n_out, int max_out, float* Y, int ldy, int Cout,
                               int accumulate, double* stats, float* wpack, int rows_hint, int prepacked,
-                              int* zero_sync, const int* tile_win, void* stream_) {
+                              int* zero_sync, const int* tile_win, const int* tile_tbl, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(gp_conv_tc_supported(Cin, Cout, K, ldx, ldy), "gp_conv_tc_fwd: unsupported shape Cin=%d Cout=%d K=%d",
                  Cin, Cout, K);
@@ -937,8 +986,27 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
         const size_t left = budget > fixed + 2 * G * b_bytes ? budget - fixed - 2 * G * b_bytes : 0;
         win_cap = (int)((left / 2) / row_b);
         win_cap &= ~7;
-        if (win_cap > 640) win_cap = 640;
+        if (win_cap > 2048) win_cap = 2048;
         if (!tm_ok || win_cap < 256) use_win = false;
+    }
+    p.ns_feed = 32;
+    p.ns_mma = 20;
+    {
+        const char* e = getenv("GAPART_TC_NS");
+        if (e) sscanf(e, "%d,%d", &p.ns_feed, &p.ns_mma);
+    }
+    static int cw_enabled = -1;
+    if (cw_enabled < 0) {
+        const char* e = getenv("GAPART_CONV_WIN");
+        cw_enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (cw_enabled && use_win && K == 27 && tile_tbl != nullptr && (reinterpret_cast<size_t>(tile_tbl) & 15) == 0) {
+        const int rc = conv_win_launch(X, Cin, wpack, tile_tbl, tile_win, d_n_out, max_out, Y, ldy, Cout, accumulate, stats,
+                                       n_chunks, p.ts, p.ns_feed, p.ns_mma, stream);
+        if (rc != GP_ERR_UNSUPPORTED) {
+            if (rc == GP_OK && !prepacked) gp_note_launch(1);
+            return rc;
+        }
     }
     const int G = use_win ? 3 : 2;
     // Operand ring of G * spg stages: a stage = 64 TMEM columns (A hi 32 | lo 32) + one weight image in
@@ -953,6 +1021,7 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
                  "gp_conv_tc_fwd: Cout=%d exceeds tensor / shared memory", Cout);
     p.inv_cin = (uint32_t)(0x100000000ull / (unsigned)Cin) + 1u;
     p.win = use_win ? tile_win : nullptr;
+    p.tile_tbl = (p.idx_bulk && tile_tbl && (reinterpret_cast<size_t>(tile_tbl) & 15) == 0) ? tile_tbl : nullptr;
     p.win_cap = win_cap;
     p.win_bytes = use_win ? (int)(((size_t)win_cap * Cin * 4 + 127) & ~(size_t)127) : 0;
     size_t smem = fixed + (size_t)p.spg * G * b_bytes + 2 * (size_t)p.win_bytes;
@@ -963,12 +1032,6 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
         configured = true;
     }
     int launches = prepacked ? 1 : 2;
-    p.ns_feed = 32;
-    p.ns_mma = 20;
-    {
-        const char* e = getenv("GAPART_TC_NS");
-        if (e) sscanf(e, "%d,%d", &p.ns_feed, &p.ns_mma);
-    }
     p.zero_sync = nullptr;
     if (ksplit > 1) {
         if (!accumulate && zero_sync) {
@@ -999,7 +1062,8 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
 // of rows up to the largest one.  One warp per tile; the table of a level is shared by every conv (forward and input
 // gradient: tap k <-> K-1-k permutes the entries of a row, the SET of neighbours is the same) of the step.
 __global__ void __launch_bounds__(256) k_tile_windows(const int* __restrict__ nbr, int tbl_stride, int K,
-                                                      const int* __restrict__ d_n, int max_rows, int* __restrict__ win) {
+                                                      const int* __restrict__ d_n, int max_rows, int* __restrict__ win,
+                                                      int* __restrict__ tile_tbl) {
     gp_pdl_wait();
     gp_pdl_trigger();
     const int n = gp_rows(d_n, max_rows);
@@ -1008,15 +1072,18 @@ __global__ void __launch_bounds__(256) k_tile_windows(const int* __restrict__ nb
     if (tile >= n_tiles) return;
     const int r0 = tile * TC_ROWS;
     int lo = 0x7fffffff, hi = -1;
+    int* tt = tile_tbl ? tile_tbl + (size_t)tile * K * TC_ROWS : nullptr;
     for (int k = 0; k < K; ++k) {
         const int* row = nbr + (size_t)k * tbl_stride + r0;
 #pragma unroll
         for (int j = 0; j < TC_ROWS / 32; ++j) {
             const int r = j * 32 + lane;
+            int v = -1;
             if (r0 + r < n) {
-                const int v = __ldg(row + r);
+                v = __ldg(row + r);
                 if (v >= 0) { lo = min(lo, v); hi = max(hi, v); }
             }
+            if (tt) tt[k * TC_ROWS + r] = v;    // rows beyond the device count: no pair
         }
     }
     lo = __reduce_min_sync(0xffffffffu, lo);
@@ -1028,12 +1095,12 @@ __global__ void __launch_bounds__(256) k_tile_windows(const int* __restrict__ nb
 }
 
 extern "C" int gp_tile_windows(const int* nbr, int tbl_stride, int K, const int* d_n, int max_rows, int* tile_win,
-                               void* stream_) {
+                               int* tile_tbl, void* stream_) {
     GP_CHECK_ARG(nbr != nullptr && tile_win != nullptr && K >= 1 && max_rows >= 0, "gp_tile_windows: bad arguments");
     if (max_rows == 0) return GP_OK;
     const int tiles = gp_cdiv(max_rows, TC_ROWS);
     GP_CUDA(gp_launch(k_tile_windows, dim3(gp_cdiv((long long)tiles * 32, 256)), dim3(256), 0, (cudaStream_t)stream_, nbr,
-                      tbl_stride, K, d_n, max_rows, tile_win));
+                      tbl_stride, K, d_n, max_rows, tile_win, tile_tbl));
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;

@@ -1,0 +1,516 @@
+// SubMConv3d (27 taps) as an implicit GEMM on tcgen05 with the tile's input rows staged ONCE in shared memory.
+//
+// Same GEMM, weight images and TMEM operand layout as k_conv_tc (conv_tc.cu) - D[128 rows x Cout] += A[128 x 27*Cin] x B,
+// 3xTF32, A written to tensor memory by feeder warps, chunks of 32 K-floats - but specialised for the levels that hold
+// 84 % of the step's work (whole row tiles, rows in lexicographic order, dense rows, Cin a multiple of 16 known at
+// compile time).  What the clock64 traces of k_conv_tc showed (profiles/r2_summary.md) and what this kernel does about it:
+//   * a feeder thread executed ~410 SASS instructions per chunk (generic K/Cin/edge arithmetic, predicate spills, a
+//     branch per gathered piece) at ~5 cycles each = 2100 cycles per group and chunk.  Here Cin is a template parameter,
+//     the tile-major index table (gp_tile_windows) already holds -1 for rows past the device count, a 28th all -1 index
+//     row stands for the half chunk past the last tap, absent neighbours read a 16-byte zero block: the gather is 2
+//     index loads + 8 unconditional LDS.128, no branch; neighbours outside the window buffer take a voted slow path.
+//   * the MMA role is ONE elected thread with running stage counters (see conv_tc.cu), ~150 cycles per chunk of issue.
+//   * the loader issues 2 bulk copies per tile (window rows, index tile) + one weight image per chunk.
+// Warp roles (576 threads, 1 CTA/SM, persistent over row tiles): warps 0-3 epilogue, 4-15 feeders (3 groups x 4 TMEM
+// quadrants), 16 MMA, 17 loader.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+#include "../../include/gapart_b200.h"
+
+#define CW_ROWS 128
+#define CW_G 3
+#define CW_THREADS (32 * (4 + 4 * CW_G + 2))
+#define CW_TAPS 27
+#define CW_IDX_ROWS 28                       // 27 taps + one row of -1
+#define CW_IDXN (CW_IDX_ROWS * CW_ROWS)      // ints per index buffer
+#define CW_TMEM_COLS 512
+
+struct WinParams {
+    const float* X;
+    const float* Wpack;
+    const int* tile_tbl;     // [tile][27][128]
+    const int* win;          // [tile][2] first row, row count
+    const int* d_n_out; int max_out;
+    float* Y; int ldy; int Cout; int accumulate;
+    double* stats;
+    int n_chunks; int nbuf; int accw; int spg; int wide;
+    int win_cap; int win_bytes;
+    int ns_feed, ns_mma;
+    long long* ts;           // optional clock64 trace of CTA 0 ([12][256], same events as k_conv_tc)
+};
+
+#define CW_TS(ev, g) do { if (p.ts && blockIdx.x == 0 && lane == 0 && (g) < 256) p.ts[(ev) * 256 + (g)] = clock64(); } while (0)
+
+__device__ __forceinline__ void cw_tmem_st_16x256b_x4(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ float4 cw_lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cw_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
+    constexpr int G = CW_G;
+    constexpr int WARP_MMA = 4 + 4 * G, WARP_LOAD = WARP_MMA + 1;
+    constexpr uint32_t ROWB = CIN * 4u;
+    static_assert(CIN % 16 == 0, "a 16-float half chunk must lie inside one tap");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int Cout = p.Cout;
+    const uint32_t b_bytes = (uint32_t)Cout * 256;            // hi + lo weight image of one chunk
+    const int SA = G * p.spg;                                 // ring depth: TMEM A stages and weight images
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* tiles = smem;                                                                 // [SA] weight images
+    uint8_t* s_win = tiles + (size_t)SA * b_bytes;                                         // [2][win_bytes]
+    int* s_idx = reinterpret_cast<int*>(s_win + 2 * (size_t)p.win_bytes);                  // [2][28][128]
+    double* s_stats = reinterpret_cast<double*>(s_idx + 2 * CW_IDXN);                      // [2][Cout]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + 2 * Cout);
+    uint64_t* st_free = bars;                     // [SA]  MMAs that read stage s (TMEM A + smem B) retired
+    uint64_t* st_full = st_free + SA;             // [SA]  4 feeder warps wrote A hi/lo + the weight image landed
+    uint64_t* acc_full = st_full + SA;            // [2]
+    uint64_t* acc_empty = acc_full + 2;           // [2]
+    uint64_t* idx_full = acc_empty + 2;           // [2]   window rows + index tile of a row tile landed
+    uint64_t* idx_empty = idx_full + 2;           // [2]   every feeder warp is done with them
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(idx_empty + 2);
+    int* s_wmeta = reinterpret_cast<int*>(tmem_slot + 2);     // [2][2] first row / row count of the window buffers
+    float* s_zero = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_wmeta + 4) + 15) & ~(uintptr_t)15);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nbuf = p.nbuf;
+    const uint32_t accw = (uint32_t)p.accw;
+    const uint32_t a_base = (uint32_t)nbuf * accw;            // first TMEM column of the A stages
+
+    if (tid == 0) {
+        for (int s = 0; s < SA; ++s) {
+            mbar_init(&st_free[s], 1);
+            mbar_init(&st_full[s], 5);      // 4 feeder warps + the loader's expect_tx arrive
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);
+            mbar_init(&idx_full[b], 1);
+            mbar_init(&idx_empty[b], 4 * G);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * Cout; i += CW_THREADS) s_stats[i] = 0.0;
+    if (tid < 4) s_zero[tid] = 0.f;
+    for (int i = tid; i < 2 * CW_ROWS; i += CW_THREADS)       // index row 27 of both buffers: "no pair"
+        s_idx[(i >> 7) * CW_IDXN + CW_TAPS * CW_ROWS + (i & 127)] = -1;
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)CW_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the tail of the previous kernel; global memory is touched only from here on
+    gp_pdl_wait();
+    gp_pdl_trigger();
+    const int n_out = gp_rows(p.d_n_out, p.max_out);
+    const int n_tiles = (n_out + CW_ROWS - 1) / CW_ROWS;
+    const int n_chunks = p.n_chunks;
+
+    if (warp >= 4 && warp < WARP_MMA) {
+        // ===================== feeders: window (shared memory) -> registers -> hi/lo -> TMEM =====================
+        // group `grp` feeds the chunks with sequence number n == grp (mod G) of this CTA (the sequence runs on across
+        // tiles) into A stage grp + G * (its use count % spg).
+        const int fw = warp - 4, grp = fw >> 2, quad = fw & 3;     // quad == warp % 4 == this warp's TMEM quadrant
+        const int g = lane >> 2, q = lane & 3;
+        // TMEM lane 32*quad + 16*sub + 8*h + g (register slot s = 2*sub + h of thread (g, q)) holds tile row
+        // 32*quad + 4*g + s: a thread's 4 rows are consecutive, their 4 neighbour indices of a tap are ONE 16-byte load
+        const int rloc0 = 32 * quad + 4 * g;
+        const uint32_t t_quad = tmem_base + ((uint32_t)(32 * quad) << 16) + a_base;
+        const uint32_t zero_a = smem_u32(s_zero);
+        const int spg = p.spg;
+        const char* Xq = reinterpret_cast<const char*>(p.X) + 16 * q;
+        uint32_t use = 0;          // chunks this group has fed so far
+        uint32_t seq0 = 0;         // sequence number of the tile's first chunk
+        int titer = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer, seq0 += (uint32_t)n_chunks) {
+            const int b = titer & 1;
+            mbar_wait_warp(&idx_full[b], (uint32_t)(titer >> 1) & 1u, lane);
+            const int wlo = s_wmeta[2 * b];
+            const uint32_t wlen = (uint32_t)s_wmeta[2 * b + 1];
+            const uint32_t win_a = smem_u32(s_win) + (uint32_t)b * (uint32_t)p.win_bytes + 16u * q;
+            const uint32_t idx_a = smem_u32(s_idx + b * CW_IDXN + rloc0);
+            for (int c = (grp + G - (int)(seq0 % G)) % G; c < n_chunks; c += G) {
+                // ---- gather: K positions kk = tap*CIN + ci of the thread's left / right piece
+                const uint32_t kkL = (uint32_t)c * 32u, kkR = kkL + 16u;
+                const uint32_t tapL = kkL / CIN, tapR = kkR / CIN;
+                const uint32_t cL = (kkL - tapL * CIN) * 4u, cR = (kkR - tapR * CIN) * 4u;   // byte offset of the half in a row
+                int iL[4], iR[4];
+                lds_i32x4(idx_a + tapL * (CW_ROWS * 4u), iL);
+                lds_i32x4(idx_a + tapR * (CW_ROWS * 4u), iR);
+                float4 vL[4], vR[4];
+                bool far = false;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    // idx - wlo wraps to a huge value for idx = -1: absent and out-of-window both fail the range test
+                    const uint32_t locL = (uint32_t)(iL[s] - wlo), locR = (uint32_t)(iR[s] - wlo);
+                    const bool inL = locL < wlen, inR = locR < wlen;
+                    vL[s] = cw_lds_f32x4(inL ? win_a + cL + locL * ROWB : zero_a);
+                    vR[s] = cw_lds_f32x4(inR ? win_a + cR + locR * ROWB : zero_a);
+                    far |= (!inL && iL[s] >= 0) | (!inR && iR[s] >= 0);
+                }
+                if (__any_sync(0xffffffffu, far)) {
+                    // rare: the tile's neighbour range is longer than the window buffer
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        if (iL[s] >= 0 && (uint32_t)(iL[s] - wlo) >= wlen)
+                            vL[s] = ldg4(reinterpret_cast<const float*>(Xq + cL + (uint64_t)(uint32_t)iL[s] * ROWB));
+                        if (iR[s] >= 0 && (uint32_t)(iR[s] - wlo) >= wlen)
+                            vR[s] = ldg4(reinterpret_cast<const float*>(Xq + cR + (uint64_t)(uint32_t)iR[s] * ROWB));
+                    }
+                }
+                // ---- feed: split hi/lo, store both operands of the chunk to the TMEM stage
+                const int tn = (int)(seq0 + (uint32_t)c);   // sequence number of the chunk (trace only)
+                const uint32_t slot = use & (uint32_t)(spg - 1), round = use >> (spg - 1);   // spg is 1 or 2
+                const uint32_t sa = (uint32_t)grp + G * slot;
+                if (quad == 1) CW_TS(0, tn);
+                if (lane == 0) mbar_wait_sleep(&st_free[sa], (round & 1) ^ 1, (uint32_t)p.ns_feed);
+                __syncwarp();
+                tc_fence_after();
+                if (quad == 1) CW_TS(1, tn);
+                const uint32_t t_stage = t_quad + sa * 64u;
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    float v[16], h[16];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const float4 l = vL[2 * sub + hh], r = vR[2 * sub + hh];
+                        v[0 + 2 * hh] = l.x; v[1 + 2 * hh] = l.y; v[4 + 2 * hh] = l.z; v[5 + 2 * hh] = l.w;
+                        v[8 + 2 * hh] = r.x; v[9 + 2 * hh] = r.y; v[12 + 2 * hh] = r.z; v[13 + 2 * hh] = r.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) h[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+                    const uint32_t ta = t_stage + ((uint32_t)(16 * sub) << 16);
+                    cw_tmem_st_16x256b_x4(ta, h);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] -= h[e];
+                    cw_tmem_st_16x256b_x4(ta + 32, v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&st_full[sa]);
+                if (quad == 1) CW_TS(3, tn);
+                ++use;
+            }
+            // all index / window reads of this tile are done (their values were consumed by the stores above)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&idx_empty[b]);
+        }
+    } else if (warp == WARP_LOAD) {
+        // ===================== loader: per tile the window rows + the index tile (2 bulk copies, one tile ahead),
+        // per chunk one weight image =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t ph = 0;
+            int titer = 0, lseq = 0;
+            auto load_tile = [&](int tile, int t, bool try_only) -> bool {
+                const int b = t & 1;
+                if (t >= 2) {
+                    const uint32_t par = ((uint32_t)(t >> 1) & 1u) ^ 1u;
+                    if (try_only) {
+                        if (!mbar_test(&idx_empty[b], par)) return false;
+                    } else {
+                        mbar_wait(&idx_empty[b], par);
+                    }
+                }
+                const int wlo = __ldg(p.win + 2 * tile);
+                int wlen = __ldg(p.win + 2 * tile + 1);
+                wlen = wlen < p.win_cap ? wlen : p.win_cap;
+                const uint32_t wbytes = (uint32_t)wlen * ROWB;
+                s_wmeta[b * 2] = wlo;
+                s_wmeta[b * 2 + 1] = wlen;
+                const uint32_t ibytes = CW_TAPS * CW_ROWS * 4u;
+                const uint32_t bar = smem_u32(&idx_full[b]);
+                mbar_arrive_expect_tx(&idx_full[b], ibytes + wbytes);
+                if (wbytes) cw_bulk_g2s(smem_u32(s_win + (size_t)b * p.win_bytes), p.X + (size_t)wlo * CIN, wbytes, bar);
+                cw_bulk_g2s(smem_u32(s_idx + b * CW_IDXN), p.tile_tbl + (size_t)tile * (CW_TAPS * CW_ROWS), ibytes, bar);
+                return true;
+            };
+            if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x, 0, false);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+                const int t_next = tile + (int)gridDim.x;
+                bool pending = t_next < n_tiles;
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(&st_free[stage], ph ^ 1);
+                    if (p.ts && blockIdx.x == 0 && lseq < 256) p.ts[6 * 256 + lseq] = clock64();
+                    ++lseq;
+                    mbar_arrive_expect_tx(&st_full[stage], b_bytes);
+                    cw_bulk_g2s(smem_u32(tiles + (size_t)stage * b_bytes), p.Wpack + (size_t)c * Cout * 64, b_bytes,
+                                smem_u32(&st_full[stage]));
+                    if (++stage == SA) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
+                    if (pending) pending = !load_tile(t_next, titer + 1, true);
+                }
+                if (pending) load_tile(t_next, titer + 1, false);
+            }
+        }
+        __syncwarp();
+    } else if (warp == WARP_MMA) {
+        // ===================== MMA issuer: one elected thread (see conv_tc.cu) =====================
+        if (elect_one()) {
+            const uint32_t n_mma = p.wide ? 2u * (uint32_t)Cout : (uint32_t)Cout;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_mma >> 3) << 17) | ((uint32_t)(CW_ROWS >> 4) << 24);
+            const bool wide = p.wide != 0;
+            const uint64_t desc_hi = (uint64_t)((uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29)) << 32;
+            const uint32_t tiles16 = smem_u32(tiles) >> 4, b16 = b_bytes >> 4, lo16 = (uint32_t)Cout * 8u;
+            const uint32_t free0 = smem_u32(st_free), full0 = smem_u32(st_full);
+            const uint32_t a0 = tmem_base + a_base;
+            uint32_t sa = 0, pa = 0, seqn = 0;
+            int buf = 0;
+            uint32_t acc_ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(&acc_empty[buf], acc_ph ^ 1);
+                if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[2 * 256 + seqn] = clock64();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * accw;
+                uint32_t acc = 0;
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait_addr_sleep(full0 + sa * 8u, pa, (uint32_t)p.ns_mma);
+                    tc_fence_after();
+                    if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[4 * 256 + seqn] = clock64();
+                    const uint32_t a_hi = a0 + sa * 64u;
+                    const uint32_t bd = tiles16 + sa * b16;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t db_hi = desc_hi | (uint64_t)(bd + ks * 2);
+                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, ks == 0 ? acc : 1u);
+                        tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
+                        if (!wide) tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, desc_hi | (uint64_t)(bd + lo16 + ks * 2), idesc, 1u);
+                    }
+                    acc = 1u;
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     free0 + sa * 8u)
+                                 : "memory");
+                    if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[5 * 256 + seqn] = clock64();
+                    ++seqn;
+                    if (++sa == (uint32_t)SA) {
+                        sa = 0;
+                        pa ^= 1;
+                    }
+                }
+                tc_commit(&acc_full[buf]);
+                if (++buf == nbuf) {
+                    buf = 0;
+                    acc_ph ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 0-3): accumulator -> global rows (+ BatchNorm sum / sumsq) ==========
+        int buf = 0;
+        int eseq = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (lane == 0) mbar_wait_sleep(&acc_full[buf], acc_ph, 400);  // a whole row tile away: sleep, don't spin
+            __syncwarp();
+            tc_fence_after();
+            // TMEM lane -> tile row: the feeders' map (lane = 16*sub + 8*h + g holds row 4*g + 2*sub + h)
+            const int row = tile * CW_ROWS + warp * 32 + 4 * (lane & 7) + (lane >> 3);
+            const bool active = row < n_out;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * accw;
+            float* yr = p.Y + (size_t)row * p.ldy;
+            for (int c0 = 0; c0 < Cout; c0 += 16) {
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15])
+                    : "r"(taddr + (uint32_t)c0));
+                float f[16];
+                if (p.wide) {
+                    uint32_t v2[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+                          "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]),
+                          "=r"(v2[15])
+                        : "r"(taddr + (uint32_t)(Cout + c0)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = active ? __uint_as_float(v[e]) + __uint_as_float(v2[e]) : 0.f;
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = active ? __uint_as_float(v[e]) : 0.f;
+                }
+                if (active) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        float4* dst = reinterpret_cast<float4*>(yr + c0 + 4 * qq);
+                        float4 o = make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]);
+                        if (p.accumulate) {
+                            float4 e = *dst;
+                            o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+                            f[4 * qq] = o.x; f[4 * qq + 1] = o.y; f[4 * qq + 2] = o.z; f[4 * qq + 3] = o.w;
+                        }
+                        *dst = o;
+                    }
+                }
+                if (p.stats) {
+                    // recursive-halving column reduction over the 32 lanes: 16 shuffles per 16 columns
+                    float s8[8], q8[8];
+                    {
+                        const bool up = lane & 16;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float ms = up ? f[8 + e] : f[e], os = up ? f[e] : f[8 + e];
+                            s8[e] = ms + __shfl_xor_sync(0xffffffffu, os, 16);
+                            float mq = ms * ms, oq = os * os;
+                            q8[e] = mq + __shfl_xor_sync(0xffffffffu, oq, 16);
+                        }
+                    }
+                    float s4[4], q4[4];
+                    {
+                        const bool up = lane & 8;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float ms = up ? s8[4 + e] : s8[e], os = up ? s8[e] : s8[4 + e];
+                            s4[e] = ms + __shfl_xor_sync(0xffffffffu, os, 8);
+                            float mq = up ? q8[4 + e] : q8[e], oq = up ? q8[e] : q8[4 + e];
+                            q4[e] = mq + __shfl_xor_sync(0xffffffffu, oq, 8);
+                        }
+                    }
+                    float s2[2], q2[2];
+                    {
+                        const bool up = lane & 4;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            float ms = up ? s4[2 + e] : s4[e], os = up ? s4[e] : s4[2 + e];
+                            s2[e] = ms + __shfl_xor_sync(0xffffffffu, os, 4);
+                            float mq = up ? q4[2 + e] : q4[e], oq = up ? q4[e] : q4[2 + e];
+                            q2[e] = mq + __shfl_xor_sync(0xffffffffu, oq, 4);
+                        }
+                    }
+                    float s1, q1;
+                    {
+                        const bool up = lane & 2;
+                        float ms = up ? s2[1] : s2[0], os = up ? s2[0] : s2[1];
+                        s1 = ms + __shfl_xor_sync(0xffffffffu, os, 2);
+                        float mq = up ? q2[1] : q2[0], oq = up ? q2[0] : q2[1];
+                        q1 = mq + __shfl_xor_sync(0xffffffffu, oq, 2);
+                    }
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                    q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+                    if ((lane & 1) == 0) {
+                        int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                                  ((lane >> 1) & 1);
+                        atomicAdd(&s_stats[col], (double)s1);
+                        atomicAdd(&s_stats[Cout + col], (double)q1);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (warp == 1) CW_TS(7, eseq);
+            eseq += n_chunks;
+            if (++buf == nbuf) {
+                buf = 0;
+                acc_ph ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (p.stats) {
+        for (int i = tid; i < 2 * Cout; i += CW_THREADS) {
+            double v = s_stats[i];
+            if (v != 0.0) atomicAdd(p.stats + i, v);
+        }
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)CW_TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// launch plan: -1 = shape not covered (the caller keeps k_conv_tc), else the window capacity in rows
+static int cw_plan(int Cin, int Cout, WinParams* p, size_t* smem_out) {
+    if (!(Cin == 16 || Cin == 32 || Cin == 48 || Cin == 64) || Cout % 16 != 0 || Cout < 16 || Cout > 128) return -1;
+    const int wide = Cout <= 32 ? 1 : 0;
+    const int accw = ((wide ? 2 * Cout : Cout) + 31) & ~31;
+    const size_t b_bytes = (size_t)Cout * 256;
+    const size_t fixed = 1024 /*align*/ + (size_t)2 * CW_IDXN * 4 + (size_t)2 * Cout * 8 + 512;
+    const size_t budget = 227 * 1024;
+    const size_t row_b = (size_t)Cin * 4;
+    int best_cap = -1, best_spg = 0, best_nbuf = 0;
+    for (int spg = 2; spg >= 1; --spg) {
+        const int SA = CW_G * spg;
+        int nbuf = 0;
+        if (2 * accw + SA * 64 <= CW_TMEM_COLS) nbuf = 2;
+        else if (accw + SA * 64 <= CW_TMEM_COLS) nbuf = 1;
+        if (!nbuf || fixed + SA * b_bytes >= budget) continue;
+        int cap = (int)(((budget - fixed - SA * b_bytes) / 2) / row_b) & ~7;
+        if (cap > 2048) cap = 2048;
+        // two stages per group are worth more than a window beyond ~512 rows (mean range of a 128-row tile: 300-500)
+        if (best_cap < 0 || (best_cap < 512 && cap > best_cap)) { best_cap = cap; best_spg = spg; best_nbuf = nbuf; }
+    }
+    if (best_cap < 256) return -1;
+    p->wide = wide; p->accw = accw; p->spg = best_spg; p->nbuf = best_nbuf; p->win_cap = best_cap;
+    p->win_bytes = (int)(((size_t)best_cap * row_b + 127) & ~(size_t)127);
+    *smem_out = fixed + (size_t)CW_G * best_spg * b_bytes + 2 * (size_t)p->win_bytes;
+    return best_cap;
+}
+
+// 1 if gp_conv_tc_run takes the window kernel for this shape (given tile_win + tile_tbl and dense rows)
+extern "C" int gp_conv_win_supported(int Cin, int Cout) {
+    WinParams p;
+    size_t smem;
+    return cw_plan(Cin, Cout, &p, &smem) >= 0 ? 1 : 0;
+}
+
+// called by conv_tc_launch (conv_tc.cu); returns GP_ERR_UNSUPPORTED when the shape is not covered
+int conv_win_launch(const float* X, int Cin, const float* wpack, const int* tile_tbl, const int* tile_win, const int* d_n_out,
+                    int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats, int n_chunks, long long* ts,
+                    int ns_feed, int ns_mma, cudaStream_t stream) {
+    WinParams p;
+    size_t smem = 0;
+    if (cw_plan(Cin, Cout, &p, &smem) < 0) return GP_ERR_UNSUPPORTED;
+    p.X = X; p.Wpack = wpack; p.tile_tbl = tile_tbl; p.win = tile_win; p.d_n_out = d_n_out; p.max_out = max_out;
+    p.Y = Y; p.ldy = ldy; p.Cout = Cout; p.accumulate = accumulate; p.stats = stats; p.n_chunks = n_chunks;
+    p.ns_feed = ns_feed; p.ns_mma = ns_mma; p.ts = ts;
+    static thread_local bool configured = false;
+    if (!configured) {
+        const int budget = 227 * 1024;
+        GP_CUDA(cudaFuncSetAttribute(k_conv_win<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+        GP_CUDA(cudaFuncSetAttribute(k_conv_win<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+        GP_CUDA(cudaFuncSetAttribute(k_conv_win<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+        GP_CUDA(cudaFuncSetAttribute(k_conv_win<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+        configured = true;
+    }
+    const int sms = gp_num_sms();
+    const int tiles = gp_cdiv(max_out, CW_ROWS);
+    const int grid = tiles < sms ? tiles : sms;
+    switch (Cin) {
+        case 16: GP_CUDA(gp_launch(k_conv_win<16>, dim3(grid), dim3(CW_THREADS), smem, stream, p)); break;
+        case 32: GP_CUDA(gp_launch(k_conv_win<32>, dim3(grid), dim3(CW_THREADS), smem, stream, p)); break;
+        case 48: GP_CUDA(gp_launch(k_conv_win<48>, dim3(grid), dim3(CW_THREADS), smem, stream, p)); break;
+        default: GP_CUDA(gp_launch(k_conv_win<64>, dim3(grid), dim3(CW_THREADS), smem, stream, p)); break;
+    }
+    gp_note_launch(1);
+    GP_LAUNCH_CHECK();
+    return GP_OK;
+}

@@ -71,6 +71,19 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
         if (++polls > GP_MBAR_WATCHDOG_POLLS) mbar_timeout(addr, parity);
     }
 }
+__device__ __forceinline__ void mbar_wait_addr_sleep(uint32_t addr, uint32_t parity, uint32_t ns) {
+    uint32_t ok = 0, polls = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(ns);
+        if (++polls > GP_MBAR_WATCHDOG_POLLS) mbar_timeout(addr, parity);
+    }
+}
 #ifndef GP_MBAR_BACKOFF_NS
 #define GP_MBAR_BACKOFF_NS 32
 #endif

@@ -126,7 +126,7 @@ class SparseUNetEngine:
             if (o.B, o.shapes, o.max_rows, o.in_channels) != (self.B, self.shapes, self.max_rows, in_channels):
                 raise GapartError("levels_from: the two engines must agree on batch, shapes, row bounds and channels")
             self.coords, self.d_n, self.grids, self.scan_tmp = o.coords, o.d_n, o.grids, o.scan_tmp
-            self.nbr, self.child, self.parent8, self.win = o.nbr, o.child, o.parent8, o.win
+            self.nbr, self.child, self.parent8, self.win, self.tile_tbl = o.nbr, o.child, o.parent8, o.win, o.tile_tbl
             self.vox_feats, self.vox_cnt, self.pt_cell, self.pc_voxel_id = o.vox_feats, o.vox_cnt, o.pt_cell, o.pc_voxel_id
             self.batch_splits, self.rmin, self.rmax, self.vs = o.batch_splits, o.rmin, o.rmax, o.vs
             self.points, self.batch_offsets = o.points, o.batch_offsets
@@ -140,6 +140,9 @@ class SparseUNetEngine:
             # per 128-row tile: contiguous input-row range holding the tile's neighbours (gp_tile_windows), consumed by
             # the shared-memory window variant of the tensor-core conv
             self.win = [torch.zeros(2 * ((m + 127) // 128), dtype=torch.int32, device=dev) for m in self.max_rows]
+            # tile-major copy of the SubM tables ([tile][27][128]): a row tile's indices arrive with one bulk copy
+            self.tile_tbl = [torch.full((((m + 127) // 128) * 27 * 128,), -1, dtype=torch.int32, device=dev)
+                             for m in self.max_rows]
             self.child = [i32(8, self.max_rows[L + 1]) for L in range(depth - 1)]
             self.parent8 = [i32(8, self.max_rows[L]) for L in range(depth - 1)]
             # voxelize workspaces
@@ -277,10 +280,11 @@ class SparseUNetEngine:
         w = conv.weight
         Cout, Cin = w.shape[0], w.shape[-1]
         assert Cin == x.C, (Cin, x.C)
-        win_f = win_b = None
+        win_f = win_b = tt_f = tt_b = None
         if kind == "subm3":
             K, tbl_f, tbl_b, flip_b = 27, self.nbr[Lx], self.nbr[Lx], 1
             win_f = win_b = self.win[Lx]      # the input gradient walks the same neighbour sets (tap k <-> 26 - k)
+            tt_f = tt_b = self.tile_tbl[Lx]
         elif kind == "k1":
             K, tbl_f, tbl_b, flip_b = 1, None, None, 0
         elif kind == "down":
@@ -334,10 +338,10 @@ class SparseUNetEngine:
             if pad_in:
                 xpad[:, :Cin].copy_(x.t)     # rows beyond the device count are never read
                 C.gp_conv_tc_run(xpad.data_ptr(), Cin_p, Cin_p, pk_pad.data_ptr(), _p(tbl_f), tsf, K, _p(d_n_out),
-                                 n_out, y.ptr, y.ld, Cout, 0, st, hint, _p(eng._zero_sync), _p(win_f), s)
+                                 n_out, y.ptr, y.ld, Cout, 0, st, hint, _p(eng._zero_sync), _p(win_f), _p(tt_f), s)
             elif tc_f:
                 C.gp_conv_tc_run(x.ptr, x.ld, Cin, pk_f.data_ptr(), _p(tbl_f), tsf, K, _p(d_n_out), n_out,
-                                 y.ptr, y.ld, Cout, 0, st, hint, _p(eng._zero_sync), _p(win_f), s)
+                                 y.ptr, y.ld, Cout, 0, st, hint, _p(eng._zero_sync), _p(win_f), _p(tt_f), s)
             else:
                 C.gp_conv_fwd(x.ptr, x.ld, Cin, wp, Cin, 1, K * Cin, 0, _p(tbl_f), tsf, K, _p(d_n_out), n_out,
                               y.ptr, y.ld, Cout, 0, st, s)
@@ -394,7 +398,7 @@ class SparseUNetEngine:
                     if tc_b and dx_ld % 4 == 0:
                         C.gp_conv_tc_run(dy.ptr, dy.ld, Cout, pk_b.data_ptr(), _p(tbl_b), tsb, K,
                                          _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None,
-                                         eng.rows_hint[Lx], _p(eng._zero_sync), _p(win_b), s)
+                                         eng.rows_hint[Lx], _p(eng._zero_sync), _p(win_b), _p(tt_b), s)
                     else:
                         C.gp_conv_fwd(dy.ptr, dy.ld, Cout, wp, Cin, K * Cin, 1, flip_b, _p(tbl_b), tsb, K,
                                       _p(d_n_in), n_in, dx_ptr, dx_ld, Cin, dx_acc, None, s)
@@ -695,7 +699,8 @@ class SparseUNetEngine:
         C.gp_rulebook_subm3(_p(self.coords[L]), _p(self.d_n[L]), self.max_rows[L], self._batch_now(), *g.shape,
                             _p(g.words), _p(g.prefix), _p(g.row_of_rank), _p(self.nbr[L]),
                             self.nbr[L].shape[1], s)
-        C.gp_tile_windows(_p(self.nbr[L]), self.nbr[L].shape[1], 27, _p(self.d_n[L]), self.max_rows[L], _p(self.win[L]), s)
+        C.gp_tile_windows(_p(self.nbr[L]), self.nbr[L].shape[1], 27, _p(self.d_n[L]), self.max_rows[L], _p(self.win[L]),
+                          _p(self.tile_tbl[L]), s)
 
     def _down_table(self, L: int, s):
         g, g2 = self.grids[L], self.grids[L + 1]

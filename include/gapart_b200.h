@@ -162,14 +162,22 @@ int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w
  * separate zeroing launch; the kernel re-arms the counters before it exits.
  * tile_win (optional, from gp_tile_windows on the same table): per 128-row tile the contiguous range of input rows that
  * holds its neighbours; when given (and the launch is not K-split, rows are dense: ldx == Cin) the kernel stages that
- * range in shared memory once per tile and gathers from there instead of fetching every (row, tap) pair from L2. */
+ * range in shared memory once per tile and gathers from there instead of fetching every (row, tap) pair from L2.
+ * tile_tbl (optional, from gp_tile_windows): tile-major copy [tile][K][128] of the table, so that the K x 128 indices of a
+ * row tile arrive with ONE bulk copy instead of K (a bulk-copy issue costs ~100+ cycles whatever its size). */
 int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long total, void* stream);
 int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride, int K,
                    const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats,
-                   int rows_hint, int* zero_sync, const int* tile_win, void* stream);
+                   int rows_hint, int* zero_sync, const int* tile_win, const int* tile_tbl, void* stream);
 /* tile_win[2*t], tile_win[2*t+1] = first row / row count of the range spanned by the valid entries of rows
- * [128 t, 128 t + 128) of a pair table nbr[K][tbl_stride]; tile_win holds 2 * ceil(max_rows / 128) ints. */
-int gp_tile_windows(const int* nbr, int tbl_stride, int K, const int* d_n, int max_rows, int* tile_win, void* stream);
+ * [128 t, 128 t + 128) of a pair table nbr[K][tbl_stride]; tile_win holds 2 * ceil(max_rows / 128) ints.
+ * tile_tbl (optional): K * 128 * ceil(max_rows / 128) ints, tile_tbl[(t * K + k) * 128 + r] = nbr[k][128 t + r]
+ * (-1 for rows beyond the device count). */
+/* 1 if gp_conv_tc_run runs the specialised window kernel (conv_win.cu) for a 27-tap conv of this shape when tile_win and
+ * tile_tbl are given, rows are dense (ldx == Cin) and the launch is not K-split */
+int gp_conv_win_supported(int Cin, int Cout);
+int gp_tile_windows(const int* nbr, int tbl_stride, int K, const int* d_n, int max_rows, int* tile_win, int* tile_tbl,
+                    void* stream);
 
 /* dW(k', ci, co) += sum_i X[nbr[k][i], ci] * dY[i, co] */
 int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout,

@@ -201,7 +201,8 @@ def test_tc_index_tile_paths(cuda, cin, cout, pad):
     assert float(y2[n:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("cin,cout,shuffled", [(16, 16, False), (32, 32, False), (48, 48, False), (16, 32, True), (64, 64, False)])
+@pytest.mark.parametrize("cin,cout,shuffled", [(16, 16, False), (32, 32, False), (48, 48, False), (16, 32, True), (64, 64, False),
+                                                 (32, 16, False), (48, 96, False), (64, 128, True)])
 def test_tc_window_variant_matches(cuda, cin, cout, shuffled):
     """shared-memory window variant (gp_tile_windows + tile_win argument, 3 feeder groups) == the global-gather variant
     == fp64: rows in lexicographic order (neighbours inside the window), and rows in SHUFFLED order (ranges far longer
@@ -228,7 +229,8 @@ def test_tc_window_variant_matches(cuda, cin, cout, shuffled):
     tbl[:, :M] = nbr
     win = torch.zeros(2 * ((bound + 127) // 128), dtype=torch.int32, device=cuda)
     st = torch.cuda.current_stream().cuda_stream
-    C.gp_tile_windows(tbl.data_ptr(), bound, 27, d_n.data_ptr(), bound, win.data_ptr(), st)
+    ttbl = torch.zeros(((bound + 127) // 128) * 27 * 128, dtype=torch.int32, device=cuda)
+    C.gp_tile_windows(tbl.data_ptr(), bound, 27, d_n.data_ptr(), bound, win.data_ptr(), ttbl.data_ptr(), st)
     # windows really bracket every neighbour
     wv = win.view(-1, 2).cpu().numpy()
     nb = tbl[:, :M].cpu().numpy()
@@ -238,18 +240,20 @@ def test_tc_window_variant_matches(cuda, cin, cout, shuffled):
         assert wv[tile, 0] == v.min() and wv[tile, 0] + wv[tile, 1] - 1 == v.max()
     ws = torch.empty(int(C.gp_conv_tc_workspace_floats(27, cin, cout)), device=cuda)
     ys = []
-    for use_win in (False, True):
+    for use_win, use_tt in ((False, False), (True, True), (False, True), (True, False)):
         y = torch.full((bound, cout), 7.0, device=cuda)
         stats = torch.zeros(2 * cout, dtype=torch.float64, device=cuda)
         if not ys:   # first call packs the weights
             C.gp_conv_tc_fwd(x.data_ptr(), cin, cin, w.data_ptr(), cin, 1, 27 * cin, 0, tbl.data_ptr(), bound, 27,
                              d_n.data_ptr(), bound, y.data_ptr(), cout, cout, 0, None, ws.data_ptr(), M, st)
         C.gp_conv_tc_run(x.data_ptr(), cin, cin, ws.data_ptr(), tbl.data_ptr(), bound, 27, d_n.data_ptr(), bound,
-                         y.data_ptr(), cout, cout, 0, stats.data_ptr(), M, None, win.data_ptr() if use_win else None, st)
+                         y.data_ptr(), cout, cout, 0, stats.data_ptr(), M, None, win.data_ptr() if use_win else None,
+                         ttbl.data_ptr() if use_tt else None, st)
         torch.cuda.synchronize()
         assert bool((y[M:] == 7.0).all())                  # rows beyond the device count are untouched
         ys.append((y[:M].clone(), stats.clone()))
     ref = _ref(x[:M], w, tbl[:, :M], 27, M)
     assert rel_err(ys[1][0], ref) < 6e-5
-    assert torch.equal(ys[0][0], ys[1][0])                 # same MMAs in the same order: bit-identical
+    for other in ys[1:]:
+        assert torch.equal(ys[0][0], other[0])             # same MMAs in the same order: bit-identical
     assert rel_err(ys[1][1][:cout], ref.sum(0)) < 1e-4 and rel_err(ys[1][1][cout:], ref.square().sum(0)) < 1e-4

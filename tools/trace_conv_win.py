@@ -40,7 +40,7 @@ def run_shape(cin, cout, rows, d_n, tag):
     def launch(use_win):
         C.gp_conv_tc_run(x.data_ptr(), cin, cin, ws.data_ptr(), nbr.data_ptr(), nbr.shape[1], 27, d_n.data_ptr(),
                          eng.max_rows[0], y.data_ptr(), cout, cout, 0, None, rows, None,
-                         eng.win[0].data_ptr() if use_win else None, st)
+                         eng.win[0].data_ptr() if use_win else None, eng.tile_tbl[0].data_ptr(), st)
 
     def timeit(use_win, reps=10):
         for _ in range(3):
@@ -64,19 +64,19 @@ d1 = torch.tensor([M0 // 3], dtype=torch.int32, device=dev)
 run_shape(32, 32, M0 // 3, d1, "L1-like")
 run_shape(48, 48, M0 // 10, torch.tensor([M0 // 10], dtype=torch.int32, device=dev), "L2-like")
 
-names = ["feed", "free", "accfree", "fed", "mma0", "mma1", "wload", "epi"]
+names = ["feed", "free", "accfree", "fed", "mma0", "mma1", "wload", "epi", "w0", "w1", "mmaL", "cmt"]
 for use_win in (False, True):
-    ts = torch.zeros(8 * 256, dtype=torch.int64, device=dev)
+    ts = torch.zeros(12 * 256, dtype=torch.int64, device=dev)
     os.environ["GAPART_TC_TS"] = str(ts.data_ptr())
     for _ in range(3):
         launch(use_win)
     torch.cuda.synchronize()
     del os.environ["GAPART_TC_TS"]
-    t = ts.cpu().numpy().reshape(8, 256)
+    t = ts.cpu().numpy().reshape(12, 256)
     t0 = t[4, 0] if t[4, 0] else t[0, 0]
     print("---- trace of CTA 0,", "window" if use_win else "global-gather", "variant: cycles since the first MMA; chunk sequence numbers 28..70")
-    for gchunk in range(28, 70):
-        print(gchunk, " ".join(f"{names[e]}={int(t[e, gchunk] - t0):7d}" for e in (6, 0, 1, 3, 2, 4, 5, 7) if t[e, gchunk] != 0))
+    for gchunk in range(28, 58):
+        print(gchunk, " ".join(f"{names[e]}={int(t[e, gchunk] - t0):7d}" for e in (6, 0, 1, 3, 2, 4, 8, 9, 10, 11, 5, 7) if t[e, gchunk] != 0))
     m = t[4, 1:100]
     m = m[m != 0]
     if m.size > 2:
