@@ -628,12 +628,23 @@ __global__ void __launch_bounds__(TC_THREADS_OF(G), 1) k_conv_tc(const TcParams 
                     if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[4 * 256 + seqn] = clock64();
                     const uint32_t a_hi = a0 + sa * 64u;
                     const uint32_t bd = tiles16 + sa * b16;
+                    // two separate instruction streams: a predicated-off tcgen05.mma still costs ~50 cycles of issue
+                    // (tools/micro/mma_chunk.cu), so the third product must not sit in the wide stream as "@!p UTCHMMA"
+                    if (wide) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t db_hi = desc_hi | (uint64_t)(bd + ks * 2);
-                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, ks == 0 ? acc : 1u);
-                        tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
-                        if (!wide) tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, desc_hi | (uint64_t)(bd + lo16 + ks * 2), idesc, 1u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t db_hi = desc_hi | (uint64_t)(bd + ks * 2);
+                            tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, ks == 0 ? acc : 1u);
+                            tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t db_hi = desc_hi | (uint64_t)(bd + ks * 2);
+                            tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, ks == 0 ? acc : 1u);
+                            tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
+                            tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, desc_hi | (uint64_t)(bd + lo16 + ks * 2), idesc, 1u);
+                        }
                     }
                     acc = 1u;
                     // TMEM A stage and weight stage are reusable once these retire
@@ -1021,7 +1032,7 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
                  "gp_conv_tc_fwd: Cout=%d exceeds tensor / shared memory", Cout);
     p.inv_cin = (uint32_t)(0x100000000ull / (unsigned)Cin) + 1u;
     p.win = use_win ? tile_win : nullptr;
-    p.tile_tbl = (p.idx_bulk && tile_tbl && (reinterpret_cast<size_t>(tile_tbl) & 15) == 0) ? tile_tbl : nullptr;
+    p.tile_tbl = nullptr;   // the tile-major table holds window-relative entries: only k_conv_win reads it
     p.win_cap = win_cap;
     p.win_bytes = use_win ? (int)(((size_t)win_cap * Cin * 4 + 127) & ~(size_t)127) : 0;
     size_t smem = fixed + (size_t)p.spg * G * b_bytes + 2 * (size_t)p.win_bytes;
@@ -1072,18 +1083,15 @@ __global__ void __launch_bounds__(256) k_tile_windows(const int* __restrict__ nb
     if (tile >= n_tiles) return;
     const int r0 = tile * TC_ROWS;
     int lo = 0x7fffffff, hi = -1;
-    int* tt = tile_tbl ? tile_tbl + (size_t)tile * K * TC_ROWS : nullptr;
     for (int k = 0; k < K; ++k) {
         const int* row = nbr + (size_t)k * tbl_stride + r0;
 #pragma unroll
         for (int j = 0; j < TC_ROWS / 32; ++j) {
             const int r = j * 32 + lane;
-            int v = -1;
             if (r0 + r < n) {
-                v = __ldg(row + r);
+                const int v = __ldg(row + r);
                 if (v >= 0) { lo = min(lo, v); hi = max(hi, v); }
             }
-            if (tt) tt[k * TC_ROWS + r] = v;    // rows beyond the device count: no pair
         }
     }
     lo = __reduce_min_sync(0xffffffffu, lo);
@@ -1091,6 +1099,21 @@ __global__ void __launch_bounds__(256) k_tile_windows(const int* __restrict__ nb
     if (lane == 0) {
         win[2 * tile] = hi >= 0 ? lo : 0;
         win[2 * tile + 1] = hi >= 0 ? hi - lo + 1 : 0;
+    }
+    if (tile_tbl) {
+        // second pass (the tile's table rows are L1/L2 hits now): window-relative entries, 0 = no pair, else
+        // 1 + (row - first row of the window); rows beyond the device count have no pair
+        int* tt = tile_tbl + (size_t)tile * K * TC_ROWS;
+        for (int k = 0; k < K; ++k) {
+            const int* row = nbr + (size_t)k * tbl_stride + r0;
+#pragma unroll
+            for (int j = 0; j < TC_ROWS / 32; ++j) {
+                const int r = j * 32 + lane;
+                int v = -1;
+                if (r0 + r < n) v = __ldg(row + r);
+                tt[k * TC_ROWS + r] = v >= 0 ? v - lo + 1 : 0;
+            }
+        }
     }
 }
 

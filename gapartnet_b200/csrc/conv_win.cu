@@ -60,7 +60,96 @@ __device__ __forceinline__ void cw_bulk_g2s(uint32_t dst, const void* src, uint3
                  : "memory");
 }
 
-template <int CIN>
+// One chunk of the MMA role in ONE asm statement: probe the NEXT chunk's full barrier (non-blocking), issue this chunk's
+// MMAs and the commit, and only then read the probe's predicate.  The probe's ~100-cycle latency - serial in the issuing
+// thread, and the tensor pipe's queue is shallow (tools/micro/mma_chunk.cu: 133 cycles per 8-MMA chunk without a wait,
+// 350 with one in front of the MMAs) - overlaps the MMAs instead of preceding them.  WIDE: 2 MMAs per K step
+// (A_hi, A_lo) x [W_hi | W_lo]; else 3 (A_hi x W_hi, A_lo x W_hi, A_hi x W_lo).  Returns the probe's result.
+template <bool WIDE>
+__device__ __forceinline__ uint32_t cw_mma_chunk(uint32_t next_bar, uint32_t next_par, uint32_t d_tmem, uint32_t a_hi,
+                                                 uint64_t b_hi, uint32_t lo16, uint32_t idesc, uint32_t acc,
+                                                 uint32_t free_bar) {
+    uint32_t ready;
+    if (WIDE) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pw, pa, pt;\n\t"
+            ".reg .b32 a;\n\t"
+            ".reg .b64 b;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 pw, [%1], %2;\n\t"
+            "setp.ne.b32 pa, %7, 0;\n\t"
+            "setp.eq.b32 pt, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%4], %5, %6, pa;\n\t"
+            "add.u32 a, %4, 32;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], %5, %6, pt;\n\t"
+            "add.u64 b, %5, 2;\n\t"
+            "add.u32 a, %4, 8;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "add.u32 a, %4, 40;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "add.u64 b, %5, 4;\n\t"
+            "add.u32 a, %4, 16;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "add.u32 a, %4, 48;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "add.u64 b, %5, 6;\n\t"
+            "add.u32 a, %4, 24;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "add.u32 a, %4, 56;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+            "selp.u32 %0, 1, 0, pw;\n\t"
+            "}"
+            : "=r"(ready)
+            : "r"(next_bar), "r"(next_par), "r"(d_tmem), "r"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc), "r"(free_bar)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pw, pa, pt;\n\t"
+            ".reg .b32 a;\n\t"
+            ".reg .b64 b, bl;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 pw, [%1], %2;\n\t"
+            "setp.ne.b32 pa, %7, 0;\n\t"
+            "setp.eq.b32 pt, 0, 0;\n\t"
+            "add.u64 bl, %5, %9;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%4], %5, %6, pa;\n\t"
+            "add.u32 a, %4, 32;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], %5, %6, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%4], bl, %6, pt;\n\t"
+            "add.u64 b, %5, 2;\n\t"
+            "add.u64 bl, bl, 2;\n\t"
+            "add.u32 a, %4, 8;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], bl, %6, pt;\n\t"
+            "add.u32 a, %4, 40;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "add.u64 b, %5, 4;\n\t"
+            "add.u64 bl, bl, 2;\n\t"
+            "add.u32 a, %4, 16;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], bl, %6, pt;\n\t"
+            "add.u32 a, %4, 48;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "add.u64 b, %5, 6;\n\t"
+            "add.u64 bl, bl, 2;\n\t"
+            "add.u32 a, %4, 24;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], bl, %6, pt;\n\t"
+            "add.u32 a, %4, 56;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+            "selp.u32 %0, 1, 0, pw;\n\t"
+            "}"
+            : "=r"(ready)
+            : "r"(next_bar), "r"(next_par), "r"(d_tmem), "r"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc), "r"(free_bar),
+              "l"((uint64_t)lo16)
+            : "memory");
+    }
+    return ready;
+}
+
+template <int CIN, bool WIDE>
 __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
     constexpr int G = CW_G;
     constexpr int WARP_MMA = 4 + 4 * G, WARP_LOAD = WARP_MMA + 1;
@@ -83,8 +172,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
     uint64_t* idx_full = acc_empty + 2;           // [2]   window rows + index tile of a row tile landed
     uint64_t* idx_empty = idx_full + 2;           // [2]   every feeder warp is done with them
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(idx_empty + 2);
-    int* s_wmeta = reinterpret_cast<int*>(tmem_slot + 2);     // [2][2] first row / row count of the window buffers
-    float* s_zero = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_wmeta + 4) + 15) & ~(uintptr_t)15);
+    int* s_wmeta = reinterpret_cast<int*>(tmem_slot + 2);     // [2][4] first row, row count (capped), rows beyond the cap?
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nbuf = p.nbuf;
@@ -105,9 +193,10 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 2 * Cout; i += CW_THREADS) s_stats[i] = 0.0;
-    if (tid < 4) s_zero[tid] = 0.f;
+    // window buffer layout: [row 0 = zeros][window rows]: the tile table holds 0 for "no pair", else 1 + (row - first row)
+    if (tid < 2 * CIN) reinterpret_cast<float*>(s_win + (size_t)(tid / CIN) * p.win_bytes)[tid % CIN] = 0.f;
     for (int i = tid; i < 2 * CW_ROWS; i += CW_THREADS)       // index row 27 of both buffers: "no pair"
-        s_idx[(i >> 7) * CW_IDXN + CW_TAPS * CW_ROWS + (i & 127)] = -1;
+        s_idx[(i >> 7) * CW_IDXN + CW_TAPS * CW_ROWS + (i & 127)] = 0;
     if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)CW_TMEM_COLS));
@@ -134,7 +223,6 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
         // 32*quad + 4*g + s: a thread's 4 rows are consecutive, their 4 neighbour indices of a tap are ONE 16-byte load
         const int rloc0 = 32 * quad + 4 * g;
         const uint32_t t_quad = tmem_base + ((uint32_t)(32 * quad) << 16) + a_base;
-        const uint32_t zero_a = smem_u32(s_zero);
         const int spg = p.spg;
         const char* Xq = reinterpret_cast<const char*>(p.X) + 16 * q;
         uint32_t use = 0;          // chunks this group has fed so far
@@ -143,8 +231,9 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer, seq0 += (uint32_t)n_chunks) {
             const int b = titer & 1;
             mbar_wait_warp(&idx_full[b], (uint32_t)(titer >> 1) & 1u, lane);
-            const int wlo = s_wmeta[2 * b];
-            const uint32_t wlen = (uint32_t)s_wmeta[2 * b + 1];
+            const int wlo = s_wmeta[4 * b];
+            const uint32_t wlen = (uint32_t)s_wmeta[4 * b + 1];
+            const bool has_far = s_wmeta[4 * b + 2] != 0;     // tile-uniform: some neighbours lie beyond the window buffer
             const uint32_t win_a = smem_u32(s_win) + (uint32_t)b * (uint32_t)p.win_bytes + 16u * q;
             const uint32_t idx_a = smem_u32(s_idx + b * CW_IDXN + rloc0);
             for (int c = (grp + G - (int)(seq0 % G)) % G; c < n_chunks; c += G) {
@@ -156,24 +245,22 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
                 lds_i32x4(idx_a + tapL * (CW_ROWS * 4u), iL);
                 lds_i32x4(idx_a + tapR * (CW_ROWS * 4u), iR);
                 float4 vL[4], vR[4];
-                bool far = false;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    // idx - wlo wraps to a huge value for idx = -1: absent and out-of-window both fail the range test
-                    const uint32_t locL = (uint32_t)(iL[s] - wlo), locR = (uint32_t)(iR[s] - wlo);
-                    const bool inL = locL < wlen, inR = locR < wlen;
-                    vL[s] = cw_lds_f32x4(inL ? win_a + cL + locL * ROWB : zero_a);
-                    vR[s] = cw_lds_f32x4(inR ? win_a + cR + locR * ROWB : zero_a);
-                    far |= (!inL && iL[s] >= 0) | (!inR && iR[s] >= 0);
-                }
-                if (__any_sync(0xffffffffu, far)) {
-                    // rare: the tile's neighbour range is longer than the window buffer
+                if (!has_far) {
+                    // entry e: 0 = no pair (window row 0 is zeros), else window row e: one multiply-add per piece, no test
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
-                        if (iL[s] >= 0 && (uint32_t)(iL[s] - wlo) >= wlen)
-                            vL[s] = ldg4(reinterpret_cast<const float*>(Xq + cL + (uint64_t)(uint32_t)iL[s] * ROWB));
-                        if (iR[s] >= 0 && (uint32_t)(iR[s] - wlo) >= wlen)
-                            vR[s] = ldg4(reinterpret_cast<const float*>(Xq + cR + (uint64_t)(uint32_t)iR[s] * ROWB));
+                        vL[s] = cw_lds_f32x4(win_a + cL + (uint32_t)iL[s] * ROWB);
+                        vR[s] = cw_lds_f32x4(win_a + cR + (uint32_t)iR[s] * ROWB);
+                    }
+                } else {
+                    // rare: the tile's neighbour range is longer than the window buffer: rows beyond it come from L2
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const bool inL = (uint32_t)iL[s] <= wlen, inR = (uint32_t)iR[s] <= wlen;
+                        vL[s] = cw_lds_f32x4(win_a + cL + (inL ? (uint32_t)iL[s] : 0u) * ROWB);
+                        vR[s] = cw_lds_f32x4(win_a + cR + (inR ? (uint32_t)iR[s] : 0u) * ROWB);
+                        if (!inL) vL[s] = ldg4(reinterpret_cast<const float*>(Xq + cL + (uint64_t)(uint32_t)(wlo + iL[s] - 1) * ROWB));
+                        if (!inR) vR[s] = ldg4(reinterpret_cast<const float*>(Xq + cR + (uint64_t)(uint32_t)(wlo + iR[s] - 1) * ROWB));
                     }
                 }
                 // ---- feed: split hi/lo, store both operands of the chunk to the TMEM stage
@@ -232,15 +319,16 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
                     }
                 }
                 const int wlo = __ldg(p.win + 2 * tile);
-                int wlen = __ldg(p.win + 2 * tile + 1);
-                wlen = wlen < p.win_cap ? wlen : p.win_cap;
+                const int wfull = __ldg(p.win + 2 * tile + 1);
+                const int wlen = wfull < p.win_cap ? wfull : p.win_cap;
                 const uint32_t wbytes = (uint32_t)wlen * ROWB;
-                s_wmeta[b * 2] = wlo;
-                s_wmeta[b * 2 + 1] = wlen;
+                s_wmeta[b * 4] = wlo;
+                s_wmeta[b * 4 + 1] = wlen;
+                s_wmeta[b * 4 + 2] = wfull > wlen ? 1 : 0;
                 const uint32_t ibytes = CW_TAPS * CW_ROWS * 4u;
                 const uint32_t bar = smem_u32(&idx_full[b]);
                 mbar_arrive_expect_tx(&idx_full[b], ibytes + wbytes);
-                if (wbytes) cw_bulk_g2s(smem_u32(s_win + (size_t)b * p.win_bytes), p.X + (size_t)wlo * CIN, wbytes, bar);
+                if (wbytes) cw_bulk_g2s(smem_u32(s_win + (size_t)b * p.win_bytes) + ROWB, p.X + (size_t)wlo * CIN, wbytes, bar);
                 cw_bulk_g2s(smem_u32(s_idx + b * CW_IDXN), p.tile_tbl + (size_t)tile * (CW_TAPS * CW_ROWS), ibytes, bar);
                 return true;
             };
@@ -268,9 +356,9 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
     } else if (warp == WARP_MMA) {
         // ===================== MMA issuer: one elected thread (see conv_tc.cu) =====================
         if (elect_one()) {
-            const uint32_t n_mma = p.wide ? 2u * (uint32_t)Cout : (uint32_t)Cout;
+            const uint32_t n_mma = WIDE ? 2u * (uint32_t)Cout : (uint32_t)Cout;
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_mma >> 3) << 17) | ((uint32_t)(CW_ROWS >> 4) << 24);
-            const bool wide = p.wide != 0;
+            // descriptor high word is constant: SBO = 1024 B, version 1, SWIZZLE_128B
             const uint64_t desc_hi = (uint64_t)((uint32_t)((1024 >> 4) & 0x3FFF) | (1u << 14) | (2u << 29)) << 32;
             const uint32_t tiles16 = smem_u32(tiles) >> 4, b16 = b_bytes >> 4, lo16 = (uint32_t)Cout * 8u;
             const uint32_t free0 = smem_u32(st_free), full0 = smem_u32(st_full);
@@ -278,34 +366,28 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
             uint32_t sa = 0, pa = 0, seqn = 0;
             int buf = 0;
             uint32_t acc_ph = 0;
+            uint32_t ready = 0;                // the current chunk's full barrier was seen complete by the previous probe
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 mbar_wait(&acc_empty[buf], acc_ph ^ 1);
                 if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[2 * 256 + seqn] = clock64();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * accw;
                 uint32_t acc = 0;
                 for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait_addr_sleep(full0 + sa * 8u, pa, (uint32_t)p.ns_mma);
+                    if (!ready) mbar_wait_addr_sleep(full0 + sa * 8u, pa, (uint32_t)p.ns_mma);
                     tc_fence_after();
                     if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[4 * 256 + seqn] = clock64();
-                    const uint32_t a_hi = a0 + sa * 64u;
-                    const uint32_t bd = tiles16 + sa * b16;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t db_hi = desc_hi | (uint64_t)(bd + ks * 2);
-                        tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, db_hi, idesc, ks == 0 ? acc : 1u);
-                        tc_mma_tf32_ts(d_tmem, a_hi + 32 + ks * 8, db_hi, idesc, 1u);
-                        if (!wide) tc_mma_tf32_ts(d_tmem, a_hi + ks * 8, desc_hi | (uint64_t)(bd + lo16 + ks * 2), idesc, 1u);
+                    uint32_t sn = sa + 1, pn = pa;
+                    if (sn == (uint32_t)SA) {
+                        sn = 0;
+                        pn ^= 1;
                     }
+                    ready = cw_mma_chunk<WIDE>(full0 + sn * 8u, pn, d_tmem, a0 + sa * 64u, desc_hi | (uint64_t)(tiles16 + sa * b16),
+                                               lo16, idesc, acc, free0 + sa * 8u);
                     acc = 1u;
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     free0 + sa * 8u)
-                                 : "memory");
                     if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[5 * 256 + seqn] = clock64();
                     ++seqn;
-                    if (++sa == (uint32_t)SA) {
-                        sa = 0;
-                        pa ^= 1;
-                    }
+                    sa = sn;
+                    pa = pn;
                 }
                 tc_commit(&acc_full[buf]);
                 if (++buf == nbuf) {
@@ -338,7 +420,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
                       "=r"(v[15])
                     : "r"(taddr + (uint32_t)c0));
                 float f[16];
-                if (p.wide) {
+                if (WIDE) {
                     uint32_t v2[16];
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -463,14 +545,14 @@ static int cw_plan(int Cin, int Cout, WinParams* p, size_t* smem_out) {
         if (2 * accw + SA * 64 <= CW_TMEM_COLS) nbuf = 2;
         else if (accw + SA * 64 <= CW_TMEM_COLS) nbuf = 1;
         if (!nbuf || fixed + SA * b_bytes >= budget) continue;
-        int cap = (int)(((budget - fixed - SA * b_bytes) / 2) / row_b) & ~7;
+        int cap = ((int)(((budget - fixed - SA * b_bytes) / 2) / row_b) - 1) & ~7;   // one row of zeros in front
         if (cap > 2048) cap = 2048;
         // two stages per group are worth more than a window beyond ~512 rows (mean range of a 128-row tile: 300-500)
         if (best_cap < 0 || (best_cap < 512 && cap > best_cap)) { best_cap = cap; best_spg = spg; best_nbuf = nbuf; }
     }
     if (best_cap < 256) return -1;
     p->wide = wide; p->accw = accw; p->spg = best_spg; p->nbuf = best_nbuf; p->win_cap = best_cap;
-    p->win_bytes = (int)(((size_t)best_cap * row_b + 127) & ~(size_t)127);
+    p->win_bytes = (int)(((size_t)(best_cap + 1) * row_b + 127) & ~(size_t)127);
     *smem_out = fixed + (size_t)CW_G * best_spg * b_bytes + 2 * (size_t)p->win_bytes;
     return best_cap;
 }
@@ -492,24 +574,35 @@ int conv_win_launch(const float* X, int Cin, const float* wpack, const int* tile
     p.X = X; p.Wpack = wpack; p.tile_tbl = tile_tbl; p.win = tile_win; p.d_n_out = d_n_out; p.max_out = max_out;
     p.Y = Y; p.ldy = ldy; p.Cout = Cout; p.accumulate = accumulate; p.stats = stats; p.n_chunks = n_chunks;
     p.ns_feed = ns_feed; p.ns_mma = ns_mma; p.ts = ts;
-    static thread_local bool configured = false;
-    if (!configured) {
-        const int budget = 227 * 1024;
-        GP_CUDA(cudaFuncSetAttribute(k_conv_win<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-        GP_CUDA(cudaFuncSetAttribute(k_conv_win<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-        GP_CUDA(cudaFuncSetAttribute(k_conv_win<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-        GP_CUDA(cudaFuncSetAttribute(k_conv_win<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-        configured = true;
-    }
     const int sms = gp_num_sms();
     const int tiles = gp_cdiv(max_out, CW_ROWS);
     const int grid = tiles < sms ? tiles : sms;
-    switch (Cin) {
-        case 16: GP_CUDA(gp_launch(k_conv_win<16>, dim3(grid), dim3(CW_THREADS), smem, stream, p)); break;
-        case 32: GP_CUDA(gp_launch(k_conv_win<32>, dim3(grid), dim3(CW_THREADS), smem, stream, p)); break;
-        case 48: GP_CUDA(gp_launch(k_conv_win<48>, dim3(grid), dim3(CW_THREADS), smem, stream, p)); break;
-        default: GP_CUDA(gp_launch(k_conv_win<64>, dim3(grid), dim3(CW_THREADS), smem, stream, p)); break;
+    const int budget = 227 * 1024;
+#define CW_CASE(CIN_, WIDE_)                                                                                          \
+    {                                                                                                                 \
+        static thread_local bool configured = false;                                                                  \
+        if (!configured) {                                                                                            \
+            GP_CUDA(cudaFuncSetAttribute(k_conv_win<CIN_, WIDE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)); \
+            configured = true;                                                                                        \
+        }                                                                                                             \
+        GP_CUDA(gp_launch(k_conv_win<CIN_, WIDE_>, dim3(grid), dim3(CW_THREADS), smem, stream, p));                   \
     }
+    if (p.wide) {
+        switch (Cin) {
+            case 16: CW_CASE(16, true) break;
+            case 32: CW_CASE(32, true) break;
+            case 48: CW_CASE(48, true) break;
+            default: CW_CASE(64, true) break;
+        }
+    } else {
+        switch (Cin) {
+            case 16: CW_CASE(16, false) break;
+            case 32: CW_CASE(32, false) break;
+            case 48: CW_CASE(48, false) break;
+            default: CW_CASE(64, false) break;
+        }
+    }
+#undef CW_CASE
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;

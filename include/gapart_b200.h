@@ -163,16 +163,18 @@ int gp_conv_tc_fwd(const float* X, int ldx, int Cin, const float* W, long long w
  * tile_win (optional, from gp_tile_windows on the same table): per 128-row tile the contiguous range of input rows that
  * holds its neighbours; when given (and the launch is not K-split, rows are dense: ldx == Cin) the kernel stages that
  * range in shared memory once per tile and gathers from there instead of fetching every (row, tap) pair from L2.
- * tile_tbl (optional, from gp_tile_windows): tile-major copy [tile][K][128] of the table, so that the K x 128 indices of a
- * row tile arrive with ONE bulk copy instead of K (a bulk-copy issue costs ~100+ cycles whatever its size). */
+ * tile_tbl (optional, from gp_tile_windows): tile-major, window-relative copy [tile][K][128] of the table: the K x 128
+ * indices of a row tile arrive with ONE bulk copy; with tile_win + tile_tbl a 27-tap conv of a shape
+ * gp_conv_win_supported() accepts runs on the specialised window kernel (conv_win.cu). */
 int gp_conv_tc_pack_batch(const void* descs, int n_desc, long long total, void* stream);
 int gp_conv_tc_run(const float* X, int ldx, int Cin, const float* wpack, const int* nbr, int tbl_stride, int K,
                    const int* d_n_out, int max_out, float* Y, int ldy, int Cout, int accumulate, double* stats,
                    int rows_hint, int* zero_sync, const int* tile_win, const int* tile_tbl, void* stream);
 /* tile_win[2*t], tile_win[2*t+1] = first row / row count of the range spanned by the valid entries of rows
  * [128 t, 128 t + 128) of a pair table nbr[K][tbl_stride]; tile_win holds 2 * ceil(max_rows / 128) ints.
- * tile_tbl (optional): K * 128 * ceil(max_rows / 128) ints, tile_tbl[(t * K + k) * 128 + r] = nbr[k][128 t + r]
- * (-1 for rows beyond the device count). */
+ * tile_tbl (optional): K * 128 * ceil(max_rows / 128) ints, tile_tbl[(t * K + k) * 128 + r] = 0 if nbr[k][128 t + r] < 0
+ * (or the row lies beyond the device count), else 1 + nbr[k][128 t + r] - tile_win[2 t]: window-relative, so that a
+ * shared-memory window whose row 0 is all zeros is indexed without a range test. */
 /* 1 if gp_conv_tc_run runs the specialised window kernel (conv_win.cu) for a 27-tap conv of this shape when tile_win and
  * tile_tbl are given, rows are dense (ldx == Cin) and the launch is not K-split */
 int gp_conv_win_supported(int Cin, int Cout);

@@ -76,7 +76,7 @@ for use_win in (False, True):
     t0 = t[4, 0] if t[4, 0] else t[0, 0]
     print("---- trace of CTA 0,", "window" if use_win else "global-gather", "variant: cycles since the first MMA; chunk sequence numbers 28..70")
     for gchunk in range(28, 58):
-        print(gchunk, " ".join(f"{names[e]}={int(t[e, gchunk] - t0):7d}" for e in (6, 0, 1, 3, 2, 4, 8, 9, 10, 11, 5, 7) if t[e, gchunk] != 0))
+        print(gchunk, " ".join(f"{names[e]}={int(t[e, gchunk] - t0):7d}" for e in (6, 0, 1, 3, 2, 8, 9, 4, 10, 11, 5, 7) if t[e, gchunk] != 0))
     m = t[4, 1:100]
     m = m[m != 0]
     if m.size > 2:
