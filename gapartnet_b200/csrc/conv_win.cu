@@ -35,12 +35,14 @@ struct WinParams {
     float* Y; int ldy; int Cout; int accumulate;
     double* stats;
     int n_chunks; int nbuf; int accw; int spg; int wide;
+    int wslots, wgrp;        // weight ring: wslots groups of wgrp (2 or 4) chunks, one bulk copy per group (a bulk copy costs
+                             // ~340 cycles of the issuing thread whatever its size); (wslots - 1) * wgrp < G * spg
     int win_cap; int win_bytes;
     int ns_feed, ns_mma;
     long long* ts;           // optional clock64 trace of CTA 0 ([12][256], same events as k_conv_tc)
 };
 
-#define CW_TS(ev, g) do { if (p.ts && blockIdx.x == 0 && lane == 0 && (g) < 256) p.ts[(ev) * 256 + (g)] = clock64(); } while (0)
+#define CW_TS(ev, g) do { if (TRACE && p.ts && blockIdx.x == 0 && lane == 0 && (g) < 256) p.ts[(ev) * 256 + (g)] = clock64(); } while (0)
 
 __device__ __forceinline__ void cw_tmem_st_16x256b_x4(uint32_t taddr, const float* v) {
     asm volatile(
@@ -60,96 +62,88 @@ __device__ __forceinline__ void cw_bulk_g2s(uint32_t dst, const void* src, uint3
                  : "memory");
 }
 
-// One chunk of the MMA role in ONE asm statement: probe the NEXT chunk's full barrier (non-blocking), issue this chunk's
-// MMAs and the commit, and only then read the probe's predicate.  The probe's ~100-cycle latency - serial in the issuing
-// thread, and the tensor pipe's queue is shallow (tools/micro/mma_chunk.cu: 133 cycles per 8-MMA chunk without a wait,
-// 350 with one in front of the MMAs) - overlaps the MMAs instead of preceding them.  WIDE: 2 MMAs per K step
-// (A_hi, A_lo) x [W_hi | W_lo]; else 3 (A_hi x W_hi, A_lo x W_hi, A_hi x W_lo).  Returns the probe's result.
-template <bool WIDE>
+// The MMAs of one chunk (32 K-floats) in ONE asm statement.  WIDE: 2 MMAs per K step, (A_hi, A_lo) x [W_hi | W_lo]; else 3
+// (A_hi x W_hi, A_lo x W_hi, A_hi x W_lo).  SYNC (the second chunk of a stage pair): the statement starts with a
+// non-blocking probe of the NEXT pair's full barrier and ends with the commit that frees this pair and the read of the
+// probe's predicate - the probe's latency overlaps the MMAs instead of preceding them.  What the micro-benchmark
+// (tools/micro/mma_chunk.cu) showed about the issuing thread: 8 MMAs + commit issue in 65 cycles and the pipe runs a
+// chunk in 133, but ANY load whose result feeds a branch between two chunks costs 100-250 cycles of tensor-pipe idle
+// time, and a predicated-off tcgen05.mma still costs ~50 cycles.  Hence one synchronisation point per PAIR of chunks
+// and separate instruction streams for the two MMA shapes.
+#define CW_ASM_HEAD "{\n\t.reg .pred pw, pa, pt;\n\t.reg .b32 a;\n\t.reg .b64 b, bl;\n\t"
+#define CW_ASM_PROBE "mbarrier.test_wait.parity.shared::cta.b64 pw, [%1], %2;\n\t"
+#define CW_ASM_PRED "setp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+#define CW_MMA(A, B, P) "tcgen05.mma.cta_group::1.kind::tf32 [%3], [" A "], " B ", %6, " P ";\n\t"
+#define CW_ASM_MMAS_WIDE                                                                              \
+    CW_MMA("%4", "%5", "pa") "add.u32 a, %4, 32;\n\t" CW_MMA("a", "%5", "pt")                         \
+    "add.u64 b, %5, 2;\n\tadd.u32 a, %4, 8;\n\t" CW_MMA("a", "b", "pt") "add.u32 a, %4, 40;\n\t" CW_MMA("a", "b", "pt")  \
+    "add.u64 b, %5, 4;\n\tadd.u32 a, %4, 16;\n\t" CW_MMA("a", "b", "pt") "add.u32 a, %4, 48;\n\t" CW_MMA("a", "b", "pt") \
+    "add.u64 b, %5, 6;\n\tadd.u32 a, %4, 24;\n\t" CW_MMA("a", "b", "pt") "add.u32 a, %4, 56;\n\t" CW_MMA("a", "b", "pt")
+#define CW_ASM_MMAS_3X                                                                                \
+    "add.u64 bl, %5, %9;\n\t" CW_MMA("%4", "%5", "pa") "add.u32 a, %4, 32;\n\t" CW_MMA("a", "%5", "pt") CW_MMA("%4", "bl", "pt") \
+    "add.u64 b, %5, 2;\n\tadd.u64 bl, bl, 2;\n\tadd.u32 a, %4, 8;\n\t" CW_MMA("a", "b", "pt") CW_MMA("a", "bl", "pt")      \
+    "add.u32 a, %4, 40;\n\t" CW_MMA("a", "b", "pt")                                                  \
+    "add.u64 b, %5, 4;\n\tadd.u64 bl, bl, 2;\n\tadd.u32 a, %4, 16;\n\t" CW_MMA("a", "b", "pt") CW_MMA("a", "bl", "pt")     \
+    "add.u32 a, %4, 48;\n\t" CW_MMA("a", "b", "pt")                                                  \
+    "add.u64 b, %5, 6;\n\tadd.u64 bl, bl, 2;\n\tadd.u32 a, %4, 24;\n\t" CW_MMA("a", "b", "pt") CW_MMA("a", "bl", "pt")     \
+    "add.u32 a, %4, 56;\n\t" CW_MMA("a", "b", "pt")
+#define CW_ASM_COMMIT "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\tselp.u32 %0, 1, 0, pw;\n\t}"
+#define CW_ASM_PLAIN "mov.u32 %0, 0;\n\t}"
+#define CW_ASM_OPERANDS                                                                                                  \
+    : "=r"(ready)                                                                                                        \
+    : "r"(next_bar), "r"(next_par), "r"(d_tmem), "r"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc), "r"(free_bar), "l"((uint64_t)lo16) \
+    : "memory"
+template <bool WIDE, bool SYNC>
 __device__ __forceinline__ uint32_t cw_mma_chunk(uint32_t next_bar, uint32_t next_par, uint32_t d_tmem, uint32_t a_hi,
                                                  uint64_t b_hi, uint32_t lo16, uint32_t idesc, uint32_t acc,
                                                  uint32_t free_bar) {
     uint32_t ready;
-    if (WIDE) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred pw, pa, pt;\n\t"
-            ".reg .b32 a;\n\t"
-            ".reg .b64 b;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 pw, [%1], %2;\n\t"
-            "setp.ne.b32 pa, %7, 0;\n\t"
-            "setp.eq.b32 pt, 0, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%4], %5, %6, pa;\n\t"
-            "add.u32 a, %4, 32;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], %5, %6, pt;\n\t"
-            "add.u64 b, %5, 2;\n\t"
-            "add.u32 a, %4, 8;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "add.u32 a, %4, 40;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "add.u64 b, %5, 4;\n\t"
-            "add.u32 a, %4, 16;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "add.u32 a, %4, 48;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "add.u64 b, %5, 6;\n\t"
-            "add.u32 a, %4, 24;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "add.u32 a, %4, 56;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-            "selp.u32 %0, 1, 0, pw;\n\t"
-            "}"
-            : "=r"(ready)
-            : "r"(next_bar), "r"(next_par), "r"(d_tmem), "r"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc), "r"(free_bar)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred pw, pa, pt;\n\t"
-            ".reg .b32 a;\n\t"
-            ".reg .b64 b, bl;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 pw, [%1], %2;\n\t"
-            "setp.ne.b32 pa, %7, 0;\n\t"
-            "setp.eq.b32 pt, 0, 0;\n\t"
-            "add.u64 bl, %5, %9;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%4], %5, %6, pa;\n\t"
-            "add.u32 a, %4, 32;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], %5, %6, pt;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%4], bl, %6, pt;\n\t"
-            "add.u64 b, %5, 2;\n\t"
-            "add.u64 bl, bl, 2;\n\t"
-            "add.u32 a, %4, 8;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], bl, %6, pt;\n\t"
-            "add.u32 a, %4, 40;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "add.u64 b, %5, 4;\n\t"
-            "add.u64 bl, bl, 2;\n\t"
-            "add.u32 a, %4, 16;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], bl, %6, pt;\n\t"
-            "add.u32 a, %4, 48;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "add.u64 b, %5, 6;\n\t"
-            "add.u64 bl, bl, 2;\n\t"
-            "add.u32 a, %4, 24;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], bl, %6, pt;\n\t"
-            "add.u32 a, %4, 56;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%3], [a], b, %6, pt;\n\t"
-            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-            "selp.u32 %0, 1, 0, pw;\n\t"
-            "}"
-            : "=r"(ready)
-            : "r"(next_bar), "r"(next_par), "r"(d_tmem), "r"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc), "r"(free_bar),
-              "l"((uint64_t)lo16)
-            : "memory");
-    }
+    if (WIDE && SYNC) asm volatile(CW_ASM_HEAD CW_ASM_PROBE CW_ASM_PRED CW_ASM_MMAS_WIDE CW_ASM_COMMIT CW_ASM_OPERANDS);
+    if (WIDE && !SYNC) asm volatile(CW_ASM_HEAD CW_ASM_PRED CW_ASM_MMAS_WIDE CW_ASM_PLAIN CW_ASM_OPERANDS);
+    if (!WIDE && SYNC) asm volatile(CW_ASM_HEAD CW_ASM_PROBE CW_ASM_PRED CW_ASM_MMAS_3X CW_ASM_COMMIT CW_ASM_OPERANDS);
+    if (!WIDE && !SYNC) asm volatile(CW_ASM_HEAD CW_ASM_PRED CW_ASM_MMAS_3X CW_ASM_PLAIN CW_ASM_OPERANDS);
     return ready;
 }
 
-template <int CIN, bool WIDE>
+// Both chunks of a pair (same tile) in ONE asm statement: probe, 16 (24) MMAs, commit, read the probe.  One statement so
+// that ptxas gives every MMA its own uniform registers: a tcgen05.mma holds its uniform operands until it leaves the
+// issue queue, and re-writing them for the next chunk (R2UR / UIADD3 of a second statement) stalls the issuing thread
+// behind the previous chunk's execution - the trace showed ~200 idle cycles between two chunk statements.
+#define CW_MMA2(A, B) "tcgen05.mma.cta_group::1.kind::tf32 [%3], [" A "], " B ", %6, pt;\n\t"
+#define CW_ASM_MMAS_WIDE_B                                                                            \
+    "add.u32 a, %4, 64;\n\t" CW_MMA2("a", "%10") "add.u32 a, %4, 96;\n\t" CW_MMA2("a", "%10")        \
+    "add.u64 b, %10, 2;\n\tadd.u32 a, %4, 72;\n\t" CW_MMA2("a", "b") "add.u32 a, %4, 104;\n\t" CW_MMA2("a", "b") \
+    "add.u64 b, %10, 4;\n\tadd.u32 a, %4, 80;\n\t" CW_MMA2("a", "b") "add.u32 a, %4, 112;\n\t" CW_MMA2("a", "b") \
+    "add.u64 b, %10, 6;\n\tadd.u32 a, %4, 88;\n\t" CW_MMA2("a", "b") "add.u32 a, %4, 120;\n\t" CW_MMA2("a", "b")
+#define CW_ASM_MMAS_3X_B                                                                              \
+    "add.u64 bl, %10, %9;\n\tadd.u32 a, %4, 64;\n\t" CW_MMA2("a", "%10") CW_MMA2("a", "bl") "add.u32 a, %4, 96;\n\t" CW_MMA2("a", "%10") \
+    "add.u64 b, %10, 2;\n\tadd.u64 bl, bl, 2;\n\tadd.u32 a, %4, 72;\n\t" CW_MMA2("a", "b") CW_MMA2("a", "bl")   \
+    "add.u32 a, %4, 104;\n\t" CW_MMA2("a", "b")                                                      \
+    "add.u64 b, %10, 4;\n\tadd.u64 bl, bl, 2;\n\tadd.u32 a, %4, 80;\n\t" CW_MMA2("a", "b") CW_MMA2("a", "bl")   \
+    "add.u32 a, %4, 112;\n\t" CW_MMA2("a", "b")                                                      \
+    "add.u64 b, %10, 6;\n\tadd.u64 bl, bl, 2;\n\tadd.u32 a, %4, 88;\n\t" CW_MMA2("a", "b") CW_MMA2("a", "bl")   \
+    "add.u32 a, %4, 120;\n\t" CW_MMA2("a", "b")
+template <bool WIDE>
+__device__ __forceinline__ uint32_t cw_mma_pair(uint32_t next_bar, uint32_t next_par, uint32_t d_tmem, uint32_t a_hi,
+                                                uint64_t b_hi, uint64_t b_hi2, uint32_t lo16, uint32_t idesc, uint32_t acc,
+                                                uint32_t free_bar) {
+    uint32_t ready;
+    if (WIDE)
+        asm volatile(CW_ASM_HEAD CW_ASM_PROBE CW_ASM_PRED CW_ASM_MMAS_WIDE CW_ASM_MMAS_WIDE_B CW_ASM_COMMIT
+                     : "=r"(ready)
+                     : "r"(next_bar), "r"(next_par), "r"(d_tmem), "r"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc), "r"(free_bar),
+                       "l"((uint64_t)lo16), "l"(b_hi2)
+                     : "memory");
+    else
+        asm volatile(CW_ASM_HEAD CW_ASM_PROBE CW_ASM_PRED CW_ASM_MMAS_3X CW_ASM_MMAS_3X_B CW_ASM_COMMIT
+                     : "=r"(ready)
+                     : "r"(next_bar), "r"(next_par), "r"(d_tmem), "r"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc), "r"(free_bar),
+                       "l"((uint64_t)lo16), "l"(b_hi2)
+                     : "memory");
+    return ready;
+}
+
+template <int CIN, bool WIDE, bool TRACE>
 __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
     constexpr int G = CW_G;
     constexpr int WARP_MMA = 4 + 4 * G, WARP_LOAD = WARP_MMA + 1;
@@ -158,16 +152,19 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int Cout = p.Cout;
     const uint32_t b_bytes = (uint32_t)Cout * 256;            // hi + lo weight image of one chunk
-    const int SA = G * p.spg;                                 // ring depth: TMEM A stages and weight images
+    constexpr int SA = 6;                                     // TMEM A stages (64 columns each), used as 3 PAIRS
+    constexpr int NPB = 3;                                    // pair barriers
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* tiles = smem;                                                                 // [SA] weight images
-    uint8_t* s_win = tiles + (size_t)SA * b_bytes;                                         // [2][win_bytes]
+    const int NP = p.wslots, WG = p.wgrp;                     // weight ring: NP slots of WG chunk images
+    uint8_t* tiles = smem;                                                                 // [NP][WG] weight images
+    uint8_t* s_win = tiles + (size_t)NP * WG * b_bytes;                                    // [2][win_bytes]
     int* s_idx = reinterpret_cast<int*>(s_win + 2 * (size_t)p.win_bytes);                  // [2][28][128]
     double* s_stats = reinterpret_cast<double*>(s_idx + 2 * CW_IDXN);                      // [2][Cout]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + 2 * Cout);
-    uint64_t* st_free = bars;                     // [SA]  MMAs that read stage s (TMEM A + smem B) retired
-    uint64_t* st_full = st_free + SA;             // [SA]  4 feeder warps wrote A hi/lo + the weight image landed
-    uint64_t* acc_full = st_full + SA;            // [2]
+    // chunk sequence number n of this CTA (running on across tiles) -> A stage n % 6, pair n / 2 -> barriers (n / 2) % 3
+    uint64_t* st_free = bars;                     // [3]  the MMAs that read the pair's two A stages (+ weights) retired
+    uint64_t* st_full = st_free + NPB;            // [3]  2 x 4 feeder warps wrote A hi/lo (+ the weight group landed)
+    uint64_t* acc_full = st_full + NPB;           // [2]
     uint64_t* acc_empty = acc_full + 2;           // [2]
     uint64_t* idx_full = acc_empty + 2;           // [2]   window rows + index tile of a row tile landed
     uint64_t* idx_empty = idx_full + 2;           // [2]   every feeder warp is done with them
@@ -180,9 +177,10 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
     const uint32_t a_base = (uint32_t)nbuf * accw;            // first TMEM column of the A stages
 
     if (tid == 0) {
-        for (int s = 0; s < SA; ++s) {
+        for (int s = 0; s < NPB; ++s) {
             mbar_init(&st_free[s], 1);
-            mbar_init(&st_full[s], 5);      // 4 feeder warps + the loader's expect_tx arrive
+            mbar_init(&st_full[s], 8);      // 4 feeder warps x 2 chunks; quadrant 0 of a weight group's first chunk also
+                                            // posts the group's expect_tx (one SYNCS less per chunk in the loader thread)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -216,16 +214,15 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
     if (warp >= 4 && warp < WARP_MMA) {
         // ===================== feeders: window (shared memory) -> registers -> hi/lo -> TMEM =====================
         // group `grp` feeds the chunks with sequence number n == grp (mod G) of this CTA (the sequence runs on across
-        // tiles) into A stage grp + G * (its use count % spg).
+        // tiles) into A stage n % 6; the two chunks of a pair come from two different groups.
         const int fw = warp - 4, grp = fw >> 2, quad = fw & 3;     // quad == warp % 4 == this warp's TMEM quadrant
         const int g = lane >> 2, q = lane & 3;
         // TMEM lane 32*quad + 16*sub + 8*h + g (register slot s = 2*sub + h of thread (g, q)) holds tile row
         // 32*quad + 4*g + s: a thread's 4 rows are consecutive, their 4 neighbour indices of a tap are ONE 16-byte load
         const int rloc0 = 32 * quad + 4 * g;
         const uint32_t t_quad = tmem_base + ((uint32_t)(32 * quad) << 16) + a_base;
-        const int spg = p.spg;
+        const uint32_t total = (uint32_t)((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (uint32_t)n_chunks;
         const char* Xq = reinterpret_cast<const char*>(p.X) + 16 * q;
-        uint32_t use = 0;          // chunks this group has fed so far
         uint32_t seq0 = 0;         // sequence number of the tile's first chunk
         int titer = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer, seq0 += (uint32_t)n_chunks) {
@@ -264,11 +261,11 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
                     }
                 }
                 // ---- feed: split hi/lo, store both operands of the chunk to the TMEM stage
-                const int tn = (int)(seq0 + (uint32_t)c);   // sequence number of the chunk (trace only)
-                const uint32_t slot = use & (uint32_t)(spg - 1), round = use >> (spg - 1);   // spg is 1 or 2
-                const uint32_t sa = (uint32_t)grp + G * slot;
+                const uint32_t seq = seq0 + (uint32_t)c;    // sequence number of the chunk
+                const int tn = (int)seq;
+                const uint32_t round = seq / 6u, sa = seq - 6u * round, pb = sa >> 1;   // A stage, pair barrier, its use count
                 if (quad == 1) CW_TS(0, tn);
-                if (lane == 0) mbar_wait_sleep(&st_free[sa], (round & 1) ^ 1, (uint32_t)p.ns_feed);
+                if (lane == 0) mbar_wait_sleep(&st_free[pb], (round & 1) ^ 1, (uint32_t)p.ns_feed);
                 __syncwarp();
                 tc_fence_after();
                 if (quad == 1) CW_TS(1, tn);
@@ -293,9 +290,15 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&st_full[sa]);
+                if (lane == 0) {
+                    if (quad == 0 && (c & (WG - 1)) == 0)
+                        mbar_arrive_expect_tx(&st_full[pb], (uint32_t)(n_chunks - c < WG ? n_chunks - c : WG) * b_bytes);
+                    else
+                        mbar_arrive(&st_full[pb]);
+                    // the CTA's very last chunk has no partner when the total is odd: arrive for the missing half too
+                    if (seq + 1 == total && (seq & 1u) == 0) mbar_arrive(&st_full[pb]);
+                }
                 if (quad == 1) CW_TS(3, tn);
-                ++use;
             }
             // all index / window reads of this tile are done (their values were consumed by the stores above)
             __syncwarp();
@@ -305,8 +308,6 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
         // ===================== loader: per tile the window rows + the index tile (2 bulk copies, one tile ahead),
         // per chunk one weight image =====================
         if (elect_one()) {
-            int stage = 0;
-            uint32_t ph = 0;
             int titer = 0, lseq = 0;
             auto load_tile = [&](int tile, int t, bool try_only) -> bool {
                 const int b = t & 1;
@@ -333,20 +334,31 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
                 return true;
             };
             if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x, 0, false);
+            // weight images: one bulk copy per group of WG chunks into ring slot (group counter % NP), completing on
+            // the full barrier of the group's first chunk (its quadrant-0 feeder posts the expect_tx).  The slot is free
+            // once the LAST chunk of the group that used it NP groups ago retired (st_free of that chunk's pair).
+            const int GT = (n_chunks + WG - 1) / WG;      // groups per tile
+            uint32_t gcount = 0;                                     // global group counter
+            int slot = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
                 const int t_next = tile + (int)gridDim.x;
                 bool pending = t_next < n_tiles;
-                for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait(&st_free[stage], ph ^ 1);
-                    if (p.ts && blockIdx.x == 0 && lseq < 256) p.ts[6 * 256 + lseq] = clock64();
-                    ++lseq;
-                    mbar_arrive_expect_tx(&st_full[stage], b_bytes);
-                    cw_bulk_g2s(smem_u32(tiles + (size_t)stage * b_bytes), p.Wpack + (size_t)c * Cout * 64, b_bytes,
-                                smem_u32(&st_full[stage]));
-                    if (++stage == SA) {
-                        stage = 0;
-                        ph ^= 1;
+                const uint32_t seq0 = (uint32_t)titer * (uint32_t)n_chunks;
+                for (int c = 0; c < n_chunks; c += WG, ++gcount) {
+                    if (gcount >= (uint32_t)NP) {
+                        const uint32_t go = gcount - (uint32_t)NP;                  // the group that used this slot last
+                        const uint32_t to = go / (uint32_t)GT, jo = go - to * (uint32_t)GT;
+                        uint32_t lc = (jo + 1) * (uint32_t)WG;
+                        lc = (lc < (uint32_t)n_chunks ? lc : (uint32_t)n_chunks) - 1;   // its last chunk (tile-local)
+                        const uint32_t sq = to * (uint32_t)n_chunks + lc;
+                        mbar_wait(&st_free[(sq % 6u) >> 1], (sq / 6u) & 1u);
                     }
+                    if (TRACE && p.ts && blockIdx.x == 0 && lseq < 256) p.ts[6 * 256 + lseq] = clock64();
+                    lseq += WG;
+                    const uint32_t nch = (uint32_t)(n_chunks - c < WG ? n_chunks - c : WG);
+                    cw_bulk_g2s(smem_u32(tiles + (size_t)slot * WG * b_bytes), p.Wpack + (size_t)c * Cout * 64,
+                                nch * b_bytes, smem_u32(&st_full[((seq0 + (uint32_t)c) % 6u) >> 1]));
+                    if (++slot == NP) slot = 0;
                     if (pending) pending = !load_tile(t_next, titer + 1, true);
                 }
                 if (pending) load_tile(t_next, titer + 1, false);
@@ -363,37 +375,85 @@ __global__ void __launch_bounds__(CW_THREADS, 1) k_conv_win(const WinParams p) {
             const uint32_t tiles16 = smem_u32(tiles) >> 4, b16 = b_bytes >> 4, lo16 = (uint32_t)Cout * 8u;
             const uint32_t free0 = smem_u32(st_free), full0 = smem_u32(st_full);
             const uint32_t a0 = tmem_base + a_base;
-            uint32_t sa = 0, pa = 0, seqn = 0;
-            int buf = 0;
-            uint32_t acc_ph = 0;
-            uint32_t ready = 0;                // the current chunk's full barrier was seen complete by the previous probe
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait(&acc_empty[buf], acc_ph ^ 1);
-                if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[2 * 256 + seqn] = clock64();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * accw;
-                uint32_t acc = 0;
-                for (int c = 0; c < n_chunks; ++c) {
-                    if (!ready) mbar_wait_addr_sleep(full0 + sa * 8u, pa, (uint32_t)p.ns_mma);
-                    tc_fence_after();
-                    if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[4 * 256 + seqn] = clock64();
-                    uint32_t sn = sa + 1, pn = pa;
-                    if (sn == (uint32_t)SA) {
-                        sn = 0;
-                        pn ^= 1;
-                    }
-                    ready = cw_mma_chunk<WIDE>(full0 + sn * 8u, pn, d_tmem, a0 + sa * 64u, desc_hi | (uint64_t)(tiles16 + sa * b16),
-                                               lo16, idesc, acc, free0 + sa * 8u);
-                    acc = 1u;
-                    if (p.ts && blockIdx.x == 0 && seqn < 256) p.ts[5 * 256 + seqn] = clock64();
-                    ++seqn;
-                    sa = sn;
-                    pa = pn;
-                }
-                tc_commit(&acc_full[buf]);
+            const uint32_t slot16 = (uint32_t)WG * b16, ns_mma = (uint32_t)p.ns_mma;
+            // One synchronisation point per PAIR of chunks; every per-chunk quantity is a running register (this
+            // thread's instruction stream IS the critical path of the kernel).
+            const uint32_t total = (uint32_t)((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (uint32_t)n_chunks;
+            uint32_t seqn = 0;                 // chunk sequence number
+            uint32_t pb = 0, pa = 0;           // pair barrier index / parity
+            uint32_t a_cur = a0;               // TMEM address of the current A stage
+            uint32_t bd_cur = tiles16, cg = 0, wslot = 0;
+            int c_left = 0;                    // chunks left in the current tile (0: the next chunk opens a tile)
+            int buf = nbuf - 1;                // accumulator buffer of the current tile
+            uint32_t acc_ph = 1;               // (the first tile flips these to buffer 0, parity 0)
+            uint32_t d_tmem = 0, acc = 0;
+            uint32_t ready = 0;                // the current pair's full barrier was seen complete by the previous probe
+            auto open_tile = [&]() {           // first chunk of a tile: claim the next accumulator buffer
                 if (++buf == nbuf) {
                     buf = 0;
                     acc_ph ^= 1;
                 }
+                mbar_wait(&acc_empty[buf], acc_ph ^ 1);
+                if (TRACE && p.ts && blockIdx.x == 0 && seqn < 256) p.ts[2 * 256 + seqn] = clock64();
+                d_tmem = tmem_base + (uint32_t)buf * accw;
+                acc = 0;
+                c_left = n_chunks;
+            };
+            auto next_weights = [&]() {        // weight ring: next image of the group, or the next slot after the group's
+                bd_cur += b16;                 // / the tile's last chunk
+                if (++cg == (uint32_t)WG || c_left == 0) {
+                    cg = 0;
+                    wslot = wslot + 1 == (uint32_t)NP ? 0 : wslot + 1;
+                    bd_cur = tiles16 + wslot * slot16;
+                }
+            };
+            while (seqn < total) {
+                if (!ready) mbar_wait_addr_sleep(full0 + pb * 8u, pa, ns_mma);
+                tc_fence_after();
+                // ---- first chunk of the pair
+                if (c_left == 0) open_tile();
+                if (TRACE && p.ts && blockIdx.x == 0 && seqn < 256) p.ts[4 * 256 + seqn] = clock64();
+                const bool has_b = seqn + 1 < total;
+                uint32_t pbn = pb + 1, pn = pa;
+                if (pbn == NPB) {
+                    pbn = 0;
+                    pn ^= 1u;
+                }
+                --c_left;
+                if (has_b && c_left > 0) {
+                    // common case: both chunks belong to the same tile
+                    const uint64_t bdA = desc_hi | (uint64_t)bd_cur;
+                    next_weights();
+                    --c_left;
+                    ready = cw_mma_pair<WIDE>(full0 + pbn * 8u, pn, d_tmem, a_cur, bdA, desc_hi | (uint64_t)bd_cur, lo16, idesc, acc,
+                                              free0 + pb * 8u);
+                    acc = 1u;
+                    if (TRACE && p.ts && blockIdx.x == 0 && seqn < 256) p.ts[5 * 256 + seqn] = clock64();
+                    seqn += 2;
+                    next_weights();
+                } else if (has_b) {
+                    // the pair straddles two tiles
+                    (void)cw_mma_chunk<WIDE, false>(0, 0, d_tmem, a_cur, desc_hi | (uint64_t)bd_cur, lo16, idesc, acc, 0);
+                    ++seqn;
+                    next_weights();
+                    tc_commit(&acc_full[buf]);
+                    open_tile();
+                    --c_left;
+                    ready = cw_mma_chunk<WIDE, true>(full0 + pbn * 8u, pn, d_tmem, a_cur + 64u, desc_hi | (uint64_t)bd_cur, lo16, idesc,
+                                                     acc, free0 + pb * 8u);
+                    acc = 1u;
+                    ++seqn;
+                    next_weights();
+                } else {
+                    // the CTA's last chunk has no partner
+                    (void)cw_mma_chunk<WIDE, true>(full0 + pbn * 8u, pn, d_tmem, a_cur, desc_hi | (uint64_t)bd_cur, lo16, idesc, acc,
+                                                   free0 + pb * 8u);
+                    ++seqn;
+                }
+                if (c_left == 0) tc_commit(&acc_full[buf]);
+                a_cur = pbn == 0 ? a0 : a_cur + 128u;
+                pb = pbn;
+                pa = pn;
             }
         }
         __syncwarp();
@@ -538,22 +598,23 @@ static int cw_plan(int Cin, int Cout, WinParams* p, size_t* smem_out) {
     const size_t fixed = 1024 /*align*/ + (size_t)2 * CW_IDXN * 4 + (size_t)2 * Cout * 8 + 512;
     const size_t budget = 227 * 1024;
     const size_t row_b = (size_t)Cin * 4;
-    int best_cap = -1, best_spg = 0, best_nbuf = 0;
-    for (int spg = 2; spg >= 1; --spg) {
-        const int SA = CW_G * spg;
-        int nbuf = 0;
-        if (2 * accw + SA * 64 <= CW_TMEM_COLS) nbuf = 2;
-        else if (accw + SA * 64 <= CW_TMEM_COLS) nbuf = 1;
-        if (!nbuf || fixed + SA * b_bytes >= budget) continue;
-        int cap = ((int)(((budget - fixed - SA * b_bytes) / 2) / row_b) - 1) & ~7;   // one row of zeros in front
-        if (cap > 2048) cap = 2048;
-        // two stages per group are worth more than a window beyond ~512 rows (mean range of a 128-row tile: 300-500)
-        if (best_cap < 0 || (best_cap < 512 && cap > best_cap)) { best_cap = cap; best_spg = spg; best_nbuf = nbuf; }
-    }
+    // 6 A stages of 64 TMEM columns (3 pairs) + 1 or 2 accumulator buffers
+    int nbuf = 0;
+    if (2 * accw + 6 * 64 <= CW_TMEM_COLS) nbuf = 2;
+    else if (accw + 6 * 64 <= CW_TMEM_COLS) nbuf = 1;
+    if (!nbuf) return -1;
+    // weight ring: 2 slots of 4 chunks when they fit in 64 KB, else 3 slots of 2 chunks ((slots - 1) * group < 6)
+    int WG = 4, NP = 2;
+    if ((size_t)8 * b_bytes > 64 * 1024) { WG = 2; NP = 3; }
+    if (fixed + (size_t)NP * WG * b_bytes >= budget) return -1;
+    int best_cap = ((int)(((budget - fixed - (size_t)NP * WG * b_bytes) / 2) / row_b) - 1) & ~7;   // one row of zeros in front
+    if (best_cap > 2048) best_cap = 2048;
     if (best_cap < 256) return -1;
-    p->wide = wide; p->accw = accw; p->spg = best_spg; p->nbuf = best_nbuf; p->win_cap = best_cap;
+    p->wide = wide; p->accw = accw; p->spg = 2; p->nbuf = nbuf; p->win_cap = best_cap;
     p->win_bytes = (int)(((size_t)(best_cap + 1) * row_b + 127) & ~(size_t)127);
-    *smem_out = fixed + (size_t)CW_G * best_spg * b_bytes + 2 * (size_t)p->win_bytes;
+    p->wslots = NP;
+    p->wgrp = WG;
+    *smem_out = fixed + (size_t)NP * WG * b_bytes + 2 * (size_t)p->win_bytes;
     return best_cap;
 }
 
@@ -582,12 +643,20 @@ int conv_win_launch(const float* X, int Cin, const float* wpack, const int* tile
     {                                                                                                                 \
         static thread_local bool configured = false;                                                                  \
         if (!configured) {                                                                                            \
-            GP_CUDA(cudaFuncSetAttribute(k_conv_win<CIN_, WIDE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)); \
+            GP_CUDA(cudaFuncSetAttribute(k_conv_win<CIN_, WIDE_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)); \
             configured = true;                                                                                        \
         }                                                                                                             \
-        GP_CUDA(gp_launch(k_conv_win<CIN_, WIDE_>, dim3(grid), dim3(CW_THREADS), smem, stream, p));                   \
+        GP_CUDA(gp_launch(k_conv_win<CIN_, WIDE_, false>, dim3(grid), dim3(CW_THREADS), smem, stream, p));            \
     }
-    if (p.wide) {
+    if (p.ts && Cin == 16 && p.wide) {
+        // clock64 trace build (tools/trace_conv_win.py): only the level-0 shape is instantiated with the trace points
+        static thread_local bool configured = false;
+        if (!configured) {
+            GP_CUDA(cudaFuncSetAttribute(k_conv_win<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            configured = true;
+        }
+        GP_CUDA(gp_launch(k_conv_win<16, true, true>, dim3(grid), dim3(CW_THREADS), smem, stream, p));
+    } else if (p.wide) {
         switch (Cin) {
             case 16: CW_CASE(16, true) break;
             case 32: CW_CASE(32, true) break;

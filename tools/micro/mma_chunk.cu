@@ -66,14 +66,24 @@ __global__ void __launch_bounds__(576, 1) k(int chunks, long long* out, float* s
             const uint32_t b16 = smem_u32(sm) >> 4, bar0 = smem_u32(bar);
             uint32_t sa = 0, pa = 0;
             long long t0 = clock64();
+            long long tw = 0, ti = 0;
             for (int c = 0; c < chunks; ++c) {
+                long long ta = clock64();
                 if ((mode & 1) && c >= SA) {
-                    if (mode & 1024) {
+                    if (mode & 2048) {
+                        int r;
+                        do { asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(r) : "r"(smem_u32(&stop)) : "memory"); } while (r != 0);
+                    } else if (mode & 4096) {
+                        uint32_t ok;     // one test_wait on a barrier that is always complete (fresh barrier, parity 1), result consumed by a branch
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar0 + 30 * 8), "r"(1u) : "memory");
+                        if (!ok) __nanosleep(100);
+                    } else if (mode & 1024) {
                         int r;
                         do { asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(r) : "r"(smem_u32(&ready)) : "memory"); } while (r < c - SA + 1);
                     } else if (mode & 512) spin_test(bar0 + sa * 8, pa ^ 1);
                     else wait_bar(bar0 + sa * 8, pa ^ 1);
                 }
+                long long tb2 = clock64();
                 if (mode & 2) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a = tb + 64 + ((mode & 128) ? 0 : (sa % 6) * 64), bd = b16 + ((mode & 32) ? 0 : (sa % 6) * 256);
                 const int km = (mode & 32) ? 0 : 2, am = (mode & 128) ? 0 : 8, lm = (mode & 128) ? 0 : 32;
@@ -87,12 +97,14 @@ __global__ void __launch_bounds__(576, 1) k(int chunks, long long* out, float* s
                 }
                 if (!(mode & 64)) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + sa * 8) : "memory");
                 if (++sa == SA) { sa = 0; pa ^= 1; }
+                long long tc = clock64();
+                tw += tb2 - ta; ti += tc - tb2;
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 31 * 8) : "memory");
             long long t1 = clock64();
             wait_bar(bar0 + 31 * 8, 0);
             long long t2 = clock64();
-            if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+            if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; out[2] = tw; out[3] = ti; }
             *(volatile int*)&stop = 1;
         }
         __syncwarp();
@@ -147,25 +159,19 @@ static void run(int threads, int chunks, long long* d, float* sink) {
     k<mode, SA><<<148, threads, 98 * 1024>>>(chunks, d, sink);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
-    long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-    printf("SA %2d threads %3d mode %3d (wait %d fence %d sttm %d lds %d n16x12 %d Bfixed %d nocommit %d Afixed %d Dalt %d): issue %.1f cyc/chunk, complete %.1f cyc/chunk\n", SA, threads, mode, mode & 1, (mode >> 1) & 1,
-           (mode >> 2) & 1, (mode >> 3) & 1, (mode >> 4) & 1, (mode >> 5) & 1, (mode >> 6) & 1, (mode >> 7) & 1, (mode >> 8) & 1, (double)h[0] / chunks, (double)h[1] / chunks);
+    long long h[4]; cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
+    fflush(stdout); printf("SA %2d threads %3d mode %3d (wait %d fence %d sttm %d lds %d n16x12 %d Bfixed %d nocommit %d Afixed %d Dalt %d): issue %.1f cyc/chunk, complete %.1f cyc/chunk; wait part %.1f issue part %.1f\n", SA, threads, mode, mode & 1, (mode >> 1) & 1,
+           (mode >> 2) & 1, (mode >> 3) & 1, (mode >> 4) & 1, (mode >> 5) & 1, (mode >> 6) & 1, (mode >> 7) & 1, (mode >> 8) & 1, (double)h[0] / chunks, (double)h[1] / chunks, (double)h[2] / chunks, (double)h[3] / chunks);
 }
 int main() {
-    long long* d; cudaMalloc(&d, 16);
+    long long* d; cudaMalloc(&d, 64);
     float* sink; cudaMalloc(&sink, 4096);
     const int chunks = 1024;
     run<0, 6>(576, chunks, d, sink);
-    run<3, 1>(576, chunks, d, sink);
-    run<3, 2>(576, chunks, d, sink);
-    run<3, 3>(576, chunks, d, sink);
-    run<3, 4>(576, chunks, d, sink);
     run<3, 6>(576, chunks, d, sink);
-    run<3, 8>(576, chunks, d, sink);
-    run<3, 12>(576, chunks, d, sink);
-    run<3, 16>(576, chunks, d, sink);
-    run<3, 24>(576, chunks, d, sink);
-    run<3 + 16, 1>(576, chunks, d, sink);
-    run<3 + 16, 6>(576, chunks, d, sink);
+    run<3 + 2048, 6>(576, chunks, d, sink);
+    run<3 + 4096, 6>(576, chunks, d, sink);
+    run<1 + 4096, 6>(576, chunks, d, sink);
+    run<3 + 4096 + 64, 6>(576, chunks, d, sink);
     return 0;
 }
