@@ -46,7 +46,8 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the L0 16->16 kernels from the committed `ncu --set full`
 # captures (profiles/): a capture, not a live measurement - labelled as such in the JSON line
-TRAFFIC_NCU = {"k_conv_tc": 23642880.0, "k_wgrad_tc": 32341760.0, "source": "ncu --set full capture, profiles/prof_*_r1.metrics.txt"}
+TRAFFIC_NCU = {"k_conv_win": 23635200.0, "k_wgrad_tc": 32341760.0,
+               "source": "ncu --set full captures: profiles/prof_conv_win_r2.metrics.txt, profiles/prof_wgrad_tc_r1.metrics.txt"}
 
 
 def _peaks():
@@ -120,9 +121,14 @@ class ClockSampler:
 
 
 def make_scenes(wl, n_batches: int, rank: int):
+    """4 rotating synthetic batches.  Weak scaling = identical work per rank: every rank draws the SAME batches (with
+    per-rank seeds the voxel counts differ by a few percent and the max-over-ranks time measures the slowest rank's
+    data, not the system: 5.79 ms at N = 2 with the collective switched off, GAPART_AR=none, vs 5.55 ms at N = 1).
+    GAPART_RANK_SEEDS=1 restores per-rank scenes."""
     from gapartnet_b200 import synthetic
 
-    return [[synthetic.planes(3000 + 100000 * rank + 1000 * j + i, wl["pts"]) for i in range(wl["batch"])]
+    r = rank if os.environ.get("GAPART_RANK_SEEDS") == "1" else 0
+    return [[synthetic.planes(3000 + 100000 * r + 1000 * j + i, wl["pts"]) for i in range(wl["batch"])]
             for j in range(n_batches)]
 
 
@@ -232,6 +238,8 @@ def run_ours(args):
     # gradient allreduce (a19): inside the captured graph, on the flat arena (backbone + heads in one call); the sum is
     # turned into DDP's mean by the optimizer's grad_scale (cfg4) - cfg3/cfg5 have no optimizer in the timed step
     allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    if os.environ.get("GAPART_AR") == "none":       # perf experiment: how much of the N > 1 step is the collective
+        allreduce = None
 
     load(devb[0])
     l0 = C.gp_launch_count()
@@ -319,12 +327,14 @@ def run_ours(args):
     value = pts_per_step * args.steps / (ms_res / 1e3)
     e2e_value = pts_per_step * args.steps / (ms_e2e / 1e3)
 
-    # ---- dominant kernels: the L0 SubMConv3d 16->16 launches (forward/dgrad operator k_conv_tc and the weight
+    # ---- dominant kernels: the L0 SubMConv3d 16->16 launches (forward/dgrad operator k_conv_win and the weight
     # gradient k_wgrad_tc), timed one by one with CUDA events on the launching stream -------------------------
     roof = None
     context = None
     if rank == 0:
-        M0 = level_rows[0]
+        # the tables in the engine are those of the LAST batch of the timed loop (4 rotating batches with slightly
+        # different voxel counts): take the row count that belongs to them
+        M0 = int(eng.d_n[0].item())
         x = torch.randn(eng.max_rows[0], 16, device=dev)
         y = torch.empty_like(x)
         dyv = torch.randn_like(x)
@@ -363,10 +373,10 @@ def run_ours(args):
                     "frac": round(ach / peak, 4), "traffic": None, "launch_ms": round(ms, 4),
                     "algorithmic_bytes": alg, "peak_source": peak_src}
 
-        roof = entry("k_conv_tc (L0 SubMConv3d 16->16 forward; the same kernel runs every dgrad)", t_conv)
+        roof = entry("k_conv_win<16> (L0 SubMConv3d 16->16 forward; the same kernel runs every dgrad)", t_conv)
         roof["other_kernels"] = [entry("k_wgrad_tc (L0 SubMConv3d 16->16 weight gradient)", t_wgrad)]
         if args.workload == "cfg3":      # the captures were taken on this workload's level-0 shape
-            roof["traffic"] = TRAFFIC_NCU["k_conv_tc"]
+            roof["traffic"] = TRAFFIC_NCU["k_conv_win"]
             roof["other_kernels"][0]["traffic"] = TRAFFIC_NCU["k_wgrad_tc"]
             roof["traffic_source"] = TRAFFIC_NCU["source"]
         # whole-step algorithmic traffic of the backbone against the step time
@@ -383,7 +393,8 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            step_obj._graph = None
+            _shutdown_dist()
         return
 
     cpu = None
@@ -395,7 +406,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic (planes generator, random-init weights seed 23333)",
+        "data": "synthetic (planes generator, random-init weights seed 23333; every rank runs the same 4 rotating batches)",
         "config": cfg,
         "arm": {"parallelism": f"dp{world}", "cuda_graph": not args.no_graph, "tensor_cores": "tcgen05 3xTF32, fp32 accumulate",
                 "allreduce": "NCCL sum over the flat gradient arena, inside the captured graph" if world > 1 else None,
@@ -410,9 +421,26 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "context_baselines": context,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        step_obj._graph = None
+        _shutdown_dist()
+
+
+def _shutdown_dist():
+    """leave the process group without ever hanging the launcher: a captured graph that holds NCCL kernels can block
+    destroy_process_group(); the result line is already printed, so a watchdog ends the process after 20 s"""
+    import threading
+
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+    except Exception:
+        pass
+    t.cancel()
 
 
 def context_baselines(x, w, dy, nbr, time_launch, t_ours_ms, M0):
@@ -527,7 +555,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * wl["batch"] * wl["pts"] / r["value"], 2), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (planes generator, random-init weights seed 23333)",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (planes generator, random-init weights seed 23333; every rank runs the same 4 rotating batches)",
         "config": shared_config(args.workload),
         "arm": {"what": "CPU oracle port of the same step (spconv / epic_ops are not vendored or installable: "
                         "oracle/__init__.py); one process on the host cores whatever --gpus says"},

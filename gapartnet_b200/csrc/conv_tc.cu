@@ -1072,48 +1072,43 @@ static int conv_tc_launch(const float* X, int ldx, int Cin, const float* W, long
 // win[2 * t] = smallest valid neighbour row of tile t (128 consecutive output rows) over all taps, win[2 * t + 1] = number
 // of rows up to the largest one.  One warp per tile; the table of a level is shared by every conv (forward and input
 // gradient: tap k <-> K-1-k permutes the entries of a row, the SET of neighbours is the same) of the step.
-__global__ void __launch_bounds__(256) k_tile_windows(const int* __restrict__ nbr, int tbl_stride, int K,
-                                                      const int* __restrict__ d_n, int max_rows, int* __restrict__ win,
-                                                      int* __restrict__ tile_tbl) {
+__global__ void __launch_bounds__(TC_ROWS) k_tile_windows(const int* __restrict__ nbr, int tbl_stride, int K,
+                                                          const int* __restrict__ d_n, int max_rows, int* __restrict__ win,
+                                                          int* __restrict__ tile_tbl) {
+    // one CTA per tile, thread r owns row r of the tile: its K entries are K independent coalesced loads (a warp per tile
+    // walked 4 K serial loads: 250 us at level 0, on the critical path in front of the first conv)
     gp_pdl_wait();
     gp_pdl_trigger();
+    __shared__ int s_lo[TC_ROWS / 32], s_hi[TC_ROWS / 32];
     const int n = gp_rows(d_n, max_rows);
-    const int tile = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, r = threadIdx.x, lane = r & 31, warp = r >> 5;
     const int n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
     if (tile >= n_tiles) return;
-    const int r0 = tile * TC_ROWS;
+    const int row = tile * TC_ROWS + r;
+    const bool live = row < n;
+    int v[TC_MAX_TAPS];
     int lo = 0x7fffffff, hi = -1;
-    for (int k = 0; k < K; ++k) {
-        const int* row = nbr + (size_t)k * tbl_stride + r0;
 #pragma unroll
-        for (int j = 0; j < TC_ROWS / 32; ++j) {
-            const int r = j * 32 + lane;
-            if (r0 + r < n) {
-                const int v = __ldg(row + r);
-                if (v >= 0) { lo = min(lo, v); hi = max(hi, v); }
-            }
-        }
+    for (int k = 0; k < TC_MAX_TAPS; ++k) {
+        v[k] = (live && k < K) ? __ldg(nbr + (size_t)k * tbl_stride + row) : -1;
+        if (v[k] >= 0) { lo = min(lo, v[k]); hi = max(hi, v[k]); }
     }
     lo = __reduce_min_sync(0xffffffffu, lo);
     hi = __reduce_max_sync(0xffffffffu, hi);
-    if (lane == 0) {
+    if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < TC_ROWS / 32; ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+    if (r == 0) {
         win[2 * tile] = hi >= 0 ? lo : 0;
         win[2 * tile + 1] = hi >= 0 ? hi - lo + 1 : 0;
     }
     if (tile_tbl) {
-        // second pass (the tile's table rows are L1/L2 hits now): window-relative entries, 0 = no pair, else
-        // 1 + (row - first row of the window); rows beyond the device count have no pair
-        int* tt = tile_tbl + (size_t)tile * K * TC_ROWS;
-        for (int k = 0; k < K; ++k) {
-            const int* row = nbr + (size_t)k * tbl_stride + r0;
+        // window-relative entries: 0 = no pair, else 1 + (row - first row of the window)
+        int* tt = tile_tbl + (size_t)tile * K * TC_ROWS + r;
 #pragma unroll
-            for (int j = 0; j < TC_ROWS / 32; ++j) {
-                const int r = j * 32 + lane;
-                int v = -1;
-                if (r0 + r < n) v = __ldg(row + r);
-                tt[k * TC_ROWS + r] = v >= 0 ? v - lo + 1 : 0;
-            }
-        }
+        for (int k = 0; k < TC_MAX_TAPS; ++k)
+            if (k < K) tt[k * TC_ROWS] = v[k] >= 0 ? v[k] - lo + 1 : 0;
     }
 }
 
@@ -1122,7 +1117,8 @@ extern "C" int gp_tile_windows(const int* nbr, int tbl_stride, int K, const int*
     GP_CHECK_ARG(nbr != nullptr && tile_win != nullptr && K >= 1 && max_rows >= 0, "gp_tile_windows: bad arguments");
     if (max_rows == 0) return GP_OK;
     const int tiles = gp_cdiv(max_rows, TC_ROWS);
-    GP_CUDA(gp_launch(k_tile_windows, dim3(gp_cdiv((long long)tiles * 32, 256)), dim3(256), 0, (cudaStream_t)stream_, nbr,
+    GP_CHECK_ARG(K <= TC_MAX_TAPS, "gp_tile_windows: K = %d exceeds %d taps", K, TC_MAX_TAPS);
+    GP_CUDA(gp_launch(k_tile_windows, dim3(tiles), dim3(TC_ROWS), 0, (cudaStream_t)stream_, nbr,
                       tbl_stride, K, d_n, max_rows, tile_win, tile_tbl));
     gp_note_launch(1);
     GP_LAUNCH_CHECK();

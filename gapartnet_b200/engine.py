@@ -420,6 +420,7 @@ class SparseUNetEngine:
 
             return bwd, n_launch
 
+        make_bwd.params = [conv.weight, bn.weight, bn.bias]
         self._bwd_units.append(make_bwd)
         return a
 
@@ -593,10 +594,13 @@ class SparseUNetEngine:
             self._pack_n, self._pack_total = len(self._packs), t0
         # reverse pass: instantiate backward closures in execution order
         self._bwd = []
+        self._bwd_params = []          # parameters whose gradients are final once the op (and its wgrad) has run
         for mk in reversed(self._bwd_units):
             fn, nl = mk()
             self._bwd.append(fn)
+            self._bwd_params.append(list(getattr(mk, "params", [])))
             self._n_launch_bwd += nl
+        self._bwd_hooks = {}           # op index -> callable, run right after that backward op (bwd_checkpoint())
         # gradient w.r.t. the level-0 input rows [max_rows[0], in_channels]; valid after run_backward()
         self.in_grad = self.x0.grad if self.input_needs_grad else None
 
@@ -770,11 +774,35 @@ class SparseUNetEngine:
             C.gp_memset(_p(og), 0, og.numel() * 4, s)
             C.gp_scatter_add_rows(_p(self.d_pc_feature), self.d_pc_feature.stride(0), og.shape[1],
                                   _p(self.pc_voxel_id), self.N, _p(og), og.stride(0), s)
-        for op in self._bwd:
+        hooks = self._bwd_hooks
+        for j, op in enumerate(self._bwd):
             op()
+            if j in hooks:
+                hooks[j]()
         if self._side is not None:
             self._main.wait_stream(self._side)     # join: every weight gradient is complete on return
             self._side = None
+
+    def bwd_checkpoint(self, frac: float = 0.85):
+        """-> (op index j, arena offset lo) or None: after backward op j (and the weight gradients launched so far on
+        the side stream) every gradient in flat_grad[lo:] is final and that tail holds >= frac of the arena.  The
+        backward walks the U-Net from the level-0 decoder down and back up, the arena follows module order, so the
+        finished gradients always form a tail of the arena; the deep levels - 90 % of the bytes - finish while the
+        level-0/1 encoder units, most of the backward's time, are still to run: a chunked allreduce overlaps them.
+        Register the callable with `engine._bwd_hooks[j] = fn`; it runs on the main stream's timeline (fork a
+        communication stream from `engine._main` and `engine._side` inside it)."""
+        base, total = self.flat_grad.data_ptr(), self.flat_grad.numel()
+        off_of = {id(p): (v.data_ptr() - base) // 4 for p, v in self._grad_views}
+        size_of = {id(p): (p.numel() + 3) & ~3 for p, v in self._grad_views}
+        done, lo = 0, total
+        for j, ps in enumerate(self._bwd_params):
+            for p_ in ps:
+                if id(p_) in off_of:
+                    lo = min(lo, off_of[id(p_)])
+                    done += size_of[id(p_)]
+            if done == total - lo and done >= frac * total and j + 1 < len(self._bwd):
+                return j, int(lo)
+        return None
 
     # convenience --------------------------------------------------------------------------------
     def load_points(self, points: torch.Tensor, batch_offsets: torch.Tensor):

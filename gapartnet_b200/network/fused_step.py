@@ -16,6 +16,8 @@ tests/test_fused_step_gpu.py pins it against the reference's own step (tests/gol
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional
 
 import torch
@@ -490,26 +492,60 @@ class BackboneTrainStep:
                        _p(head.bias.grad) if head.bias is not None else None, _p(self.loss), _p(self._cnt), _stream())
         eng.run_backward()
 
+    def _install_allreduce(self, allreduce):
+        """Chunked, overlapped gradient allreduce: the tail of the arena (deep U-Net levels + head, >= 85 % of the bytes)
+        is reduced on a communication stream as soon as it is final - while the level-0/1 encoder units of the backward
+        still run - and the small remainder after the backward.  Both calls sit inside the captured graph."""
+        self._allreduce = allreduce
+        self._tail_lo = None
+        eng = self.engine
+        eng._bwd_hooks.clear()
+        if allreduce is None:
+            return
+        cp = eng.bwd_checkpoint(0.85)
+        if cp is None or os.environ.get("GAPART_AR") == "single":     # "single": one call after the backward
+            return
+        j, lo = cp
+        self._tail_lo = lo
+        self._comm = torch.cuda.Stream(device=self.dev)
+
+        def fire():
+            comm = self._comm
+            comm.wait_stream(eng._main)
+            if eng._side is not None:
+                comm.wait_stream(eng._side)          # the weight gradients launched so far
+            with torch.cuda.stream(comm):
+                allreduce(self.flat_grad[lo:])
+
+        eng._bwd_hooks[j] = fire
+
+    def _finish_allreduce(self):
+        if self._allreduce is None:
+            return
+        if self._tail_lo is None:
+            self._allreduce(self.flat_grad)
+            return
+        self._allreduce(self.flat_grad[:self._tail_lo])
+        torch.cuda.current_stream().wait_stream(self._comm)
+
     def capture(self, allreduce=None):
         """2 eager warm-up steps on a side stream (running statistics advance, parameters do not: there is no optimizer
         in this step), calibration of the row hints, then one CUDA graph of forward_backward [+ allreduce]."""
+        self._install_allreduce(allreduce)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
                 self.forward_backward()
-                if allreduce is not None:
-                    allreduce(self.flat_grad)
+                self._finish_allreduce()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         counts = self.engine.calibrate()
-        self._allreduce = allreduce
         if self.use_graph:
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self.forward_backward()
-                if allreduce is not None:
-                    allreduce(self.flat_grad)
+                self._finish_allreduce()
         return counts
 
     def step(self):
@@ -517,6 +553,5 @@ class BackboneTrainStep:
             self._graph.replay()
         else:
             self.forward_backward()
-            if self._allreduce is not None:
-                self._allreduce(self.flat_grad)
+            self._finish_allreduce()
         return self.loss

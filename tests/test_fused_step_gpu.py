@@ -202,3 +202,44 @@ def test_backbone_step_with_fused_head_matches_torch(cuda):
     # backbone gradients: same engine backward from the same input gradient; two runs differ by the order noise of
     # the split-K fp32 reductions amplified by BatchNorm over the few rows of the deepest level of this small net
     assert _relL2(st.engine.flat_grad, eng.flat_grad) < 2e-2
+
+
+def test_chunked_allreduce_covers_every_gradient_exactly_once(cuda):
+    """The overlapped gradient allreduce of BackboneTrainStep (tail of the arena fired from a backward checkpoint on a
+    communication stream, remainder after the backward) with a stand-in collective that doubles its argument - what a sum
+    over two identical ranks does: every element of the arena must come out doubled exactly once, i.e. the tail was
+    final when its chunk was issued (weight gradients run on a side stream) and the two chunks tile the arena."""
+    import copy
+
+    import gapartnet_b200.spconv.pytorch as sp
+    from gapartnet_b200.network import backbone as mirror
+    from gapartnet_b200.network.fused_step import BackboneTrainStep
+
+    B, n, voxel, S = 3, 3000, 0.04, 64
+    scs = [synthetic.planes(900 + b, n) for b in range(B)]
+    torch.manual_seed(7)
+    net = mirror.build_sparse_unet(sp, 6, [16, 32, 48, 64], 2).to(cuda)
+    head = torch.nn.Linear(16, 10).to(cuda)
+    net2, head2 = copy.deepcopy(net), copy.deepcopy(head)
+    pts = torch.from_numpy(np.concatenate([s.points for s in scs])).to(cuda)
+    lab = torch.from_numpy(np.concatenate([s.sem_labels for s in scs])).to(cuda)
+    off = torch.arange(B + 1, dtype=torch.int64, device=cuda) * n
+    grads = []
+    for use_graph, (nn_, hh), ar in ((True, (net, head), lambda t: t.mul_(2.0)), (False, (net2, head2), None)):
+        st = BackboneTrainStep(nn_, hh, batch=B, num_points=B * n, voxel_size=voxel, spatial_shape=(S, S, S), use_graph=use_graph)
+        st.engine.load_points(pts, off)
+        st.labels.copy_(lab)
+        st.capture(ar)
+        if ar is not None:
+            cp = st.engine.bwd_checkpoint(0.85)
+            assert cp is not None and st._tail_lo == cp[1] and 0 < cp[1] < 0.15 * st.flat_grad.numel() + 4
+        st.step()
+        torch.cuda.synchronize()
+        grads.append(st.flat_grad.clone())
+    g2, g1 = grads
+    assert float(g1.abs().max()) > 0
+    # split-K order noise aside (2e-2 relative L2 at this size, see the test above) the doubled arena is 2 x the plain one
+    assert _relL2(g2, 2.0 * g1) < 2e-2
+    big = g1.abs() > 1e-3 * g1.abs().max()
+    ratio = g2[big] / g1[big]
+    assert float((ratio - 2.0).abs().median()) < 1e-3
