@@ -360,9 +360,16 @@ def run_ours(args):
         t_conv = time_launch(lambda: C.gp_conv_tc_run(
             x.data_ptr(), 16, 16, ws.data_ptr(), nbr.data_ptr(), nbr.shape[1], 27, dn.data_ptr(), eng.max_rows[0],
             y.data_ptr(), 16, 16, 0, None, M0, 0, eng.win[0].data_ptr(), eng.tile_tbl[0].data_ptr(), st))
-        t_wgrad = time_launch(lambda: C.gp_conv_wgrad_tc(
-            x.data_ptr(), 16, 16, dyv.data_ptr(), 16, 16, nbr.data_ptr(), nbr.shape[1], 27, dn.data_ptr(),
-            eng.max_rows[0], dw.data_ptr(), 16, 1, 27 * 16, M0, st))
+        if os.environ.get("GAPART_WGRAD_WIN", "0") == "1" and C.gp_conv_wgrad_win_supported(16, 16):
+            wg_name = "k_wgrad_win<16> (L0 SubMConv3d 16->16 weight gradient, MN-major tcgen05 operands)"
+            t_wgrad = time_launch(lambda: C.gp_conv_wgrad_win(
+                x.data_ptr(), 16, dyv.data_ptr(), 16, 16, eng.win[0].data_ptr(), eng.tile_tbl[0].data_ptr(), dn.data_ptr(),
+                eng.max_rows[0], dw.data_ptr(), 27 * 16, st))
+        else:
+            wg_name = "k_wgrad_tc (L0 SubMConv3d 16->16 weight gradient)"
+            t_wgrad = time_launch(lambda: C.gp_conv_wgrad_tc(
+                x.data_ptr(), 16, 16, dyv.data_ptr(), 16, 16, nbr.data_ptr(), nbr.shape[1], 27, dn.data_ptr(),
+                eng.max_rows[0], dw.data_ptr(), 16, 1, 27 * 16, M0, st))
         # algorithmic bytes of one launch (SURVEY 8d per-layer figure / 3 passes): X + Y (or dY) + table + W
         alg = 4.0 * (M0 * 16 + M0 * 16 + 27 * M0 + 27 * 16 * 16)
         peak, peak_src = _peaks()
@@ -374,10 +381,10 @@ def run_ours(args):
                     "algorithmic_bytes": alg, "peak_source": peak_src}
 
         roof = entry("k_conv_win<16> (L0 SubMConv3d 16->16 forward; the same kernel runs every dgrad)", t_conv)
-        roof["other_kernels"] = [entry("k_wgrad_tc (L0 SubMConv3d 16->16 weight gradient)", t_wgrad)]
+        roof["other_kernels"] = [entry(wg_name, t_wgrad)]
         if args.workload == "cfg3":      # the captures were taken on this workload's level-0 shape
             roof["traffic"] = TRAFFIC_NCU["k_conv_win"]
-            roof["other_kernels"][0]["traffic"] = TRAFFIC_NCU["k_wgrad_tc"]
+            roof["other_kernels"][0]["traffic"] = TRAFFIC_NCU["k_wgrad_tc"] if "k_wgrad_tc" in wg_name else None
             roof["traffic_source"] = TRAFFIC_NCU["source"]
         # whole-step algorithmic traffic of the backbone against the step time
         per_scene = algorithmic_bytes_per_scene([c / BATCH for c in level_rows], 1)

@@ -104,7 +104,7 @@ def check(rc: int, what: str = "") -> None:
 
 # int-returning queries (their value is an answer, not a status code)
 _QUERIES = ("gp_version", "gp_device_sms", "gp_conv_tc_supported", "gp_conv_wgrad_tc_supported",
-            "gp_conv_tc_ksplit", "gp_bn_cluster_ok", "gp_conv_win_supported")
+            "gp_conv_tc_ksplit", "gp_bn_cluster_ok", "gp_conv_win_supported", "gp_conv_wgrad_win_supported")
 
 
 class _Caller:

@@ -188,6 +188,13 @@ int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, in
 
 /* gp_conv_wgrad on the tcgen05 tensor cores (3xTF32; csrc/conv_wgrad_tc.cu). Needs KRSC weight strides
  * (w_sci == 1, w_sk == Cin), Cin % 4 == 0, Cout <= 128; rows_hint as in gp_conv_tc_fwd. */
+/* Weight gradient of a 27-tap SubMConv3d with MN-major tcgen05 operands (conv_wgrad_win.cu): the table is given as
+ * gp_tile_windows' window table + tile-major table, X has dense rows (ld = Cin).
+ * dW[co * w_sco + k * Cin + ci] += sum_r X[nbr_k(r), ci] * dY[r, co].  Replaces gp_conv_wgrad_tc for the shapes
+ * gp_conv_wgrad_win_supported() accepts (Cin in {16, 32, 64}). */
+int gp_conv_wgrad_win_supported(int Cin, int Cout);
+int gp_conv_wgrad_win(const float* X, int Cin, const float* dY, int ldy, int Cout, const int* tile_win, const int* tile_tbl,
+                      const int* d_n_out, int max_out, float* dW, long long w_sco, void* stream);
 int gp_conv_wgrad_tc_supported(int Cin, int Cout, int K, int ldx, int ldy, long long w_sk, long long w_sci);
 int gp_conv_wgrad_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, const int* nbr,
                      int tbl_stride, int K, const int* d_n_out, int max_out, float* dW, long long w_sk,

@@ -257,3 +257,47 @@ def test_tc_window_variant_matches(cuda, cin, cout, shuffled):
     for other in ys[1:]:
         assert torch.equal(ys[0][0], other[0])             # same MMAs in the same order: bit-identical
     assert rel_err(ys[1][1][:cout], ref.sum(0)) < 1e-4 and rel_err(ys[1][1][cout:], ref.square().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,shuffled", [(16, 16, False), (16, 32, False), (32, 32, False), (64, 64, False), (16, 16, True),
+                                               (32, 16, False), (16, 64, False)])
+def test_wgrad_win_matches_fp64(cuda, cin, cout, shuffled):
+    """gp_conv_wgrad_win (MN-major tcgen05 operands, SWIZZLE_128B_BASE32B; gathered rows and dY rows go into shared memory
+    as they are - no transpose) vs fp64: rows in lexicographic order, rows in SHUFFLED order (neighbour ranges far longer
+    than the window buffer: the global fall-back), a device-side row count short of the bound, accumulation into dW."""
+    from gapartnet_b200._lib import C
+
+    if not C.gp_conv_wgrad_win_supported(cin, cout):
+        pytest.skip("shape not covered by the window weight-gradient kernel on this shared-memory budget")
+    t = _table(cuda, n=9000)
+    M = t["M"]
+    nbr = t["nbr"]
+    if shuffled:
+        g0 = torch.Generator().manual_seed(3)
+        perm = torch.randperm(M, generator=g0).to(cuda)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(M, device=cuda)
+        old = nbr[:, perm].long()
+        nbr = torch.where(old >= 0, inv[old.clamp(min=0)], old).int().contiguous()
+    n = M - 77                                         # device-side count below the bound, ragged last tile
+    g = torch.Generator(device="cpu").manual_seed(cin * 31 + cout)
+    x = torch.randn(M, cin, generator=g).to(cuda)
+    dy = torch.randn(M, cout, generator=g).to(cuda)
+    tbl = torch.full((27, M), -1, dtype=torch.int32, device=cuda)
+    tbl[:, :n] = torch.where(nbr[:, :n] < n, nbr[:, :n], torch.full_like(nbr[:, :n], -1))
+    d_n = torch.tensor([n], dtype=torch.int32, device=cuda)
+    tiles = (M + 127) // 128
+    win = torch.zeros(2 * tiles, dtype=torch.int32, device=cuda)
+    ttbl = torch.zeros(tiles * 27 * 128, dtype=torch.int32, device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    C.gp_tile_windows(tbl.data_ptr(), M, 27, d_n.data_ptr(), M, win.data_ptr(), ttbl.data_ptr(), st)
+    dw = torch.full((cout, 27, cin), 0.5, device=cuda)            # accumulates on top of what is there
+    C.gp_conv_wgrad_win(x.data_ptr(), cin, dy.data_ptr(), cout, cout, win.data_ptr(), ttbl.data_ptr(), d_n.data_ptr(), M,
+                        dw.data_ptr(), 27 * cin, st)
+    torch.cuda.synchronize()
+    ref = torch.full((cout, 27, cin), 0.5, dtype=torch.float64, device=cuda)
+    for k in range(27):
+        idx = tbl[k, :n].long()
+        ok = idx >= 0
+        ref[:, k, :] += dy[:n][ok].double().t() @ x[idx[ok]].double()
+    assert rel_err(dw, ref) < 2e-5
