@@ -360,8 +360,8 @@ def run_ours(args):
         t_conv = time_launch(lambda: C.gp_conv_tc_run(
             x.data_ptr(), 16, 16, ws.data_ptr(), nbr.data_ptr(), nbr.shape[1], 27, dn.data_ptr(), eng.max_rows[0],
             y.data_ptr(), 16, 16, 0, None, M0, 0, eng.win[0].data_ptr(), eng.tile_tbl[0].data_ptr(), st))
-        if os.environ.get("GAPART_WGRAD_WIN", "0") == "1" and C.gp_conv_wgrad_win_supported(16, 16):
-            wg_name = "k_wgrad_win<16> (L0 SubMConv3d 16->16 weight gradient, MN-major tcgen05 operands)"
+        if os.environ.get("GAPART_WGRAD_WIN", "1") != "0" and C.gp_conv_wgrad_win_supported(16, 16):
+            wg_name = "k_wgrad_win (L0 SubMConv3d 16->16 weight gradient, gathered operand in TMEM)"
             t_wgrad = time_launch(lambda: C.gp_conv_wgrad_win(
                 x.data_ptr(), 16, dyv.data_ptr(), 16, 16, eng.win[0].data_ptr(), eng.tile_tbl[0].data_ptr(), dn.data_ptr(),
                 eng.max_rows[0], dw.data_ptr(), 27 * 16, st))

@@ -14,7 +14,8 @@ from typing import Dict, List, Tuple
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(ROOT, "include", "gapart_b200.h")
-LIB_PATH = os.path.join(_HERE, "libgapart_b200.so")
+# GAPART_LIB: perf tooling only (tools/perf_wgrad.py compares build variants of one kernel)
+LIB_PATH = os.environ.get("GAPART_LIB") or os.path.join(_HERE, "libgapart_b200.so")
 
 _lib = None
 _protos: Dict[str, Tuple[str, List[str]]] = {}

@@ -39,11 +39,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // Every blocking wait carries a watchdog: a protocol bug must surface as a trapped kernel with a message, never
 // as a hung GPU (legitimate waits are micro-seconds; the limit is ~1 s of polling).
 #define GP_MBAR_WATCHDOG_POLLS 40000000u
+#ifdef GP_MBAR_TRAP_INLINE
+// k_wgrad_win: the watchdog is a bare trap, NOT the printf helper: a (never taken) function call in a polling loop made
+// ptxas keep loop counters of the feeder role in local memory across it, and with the 227 KB shared-memory carve-out there
+// is no L1 left - every such LDL/STL is an L2 round trip (~1400 idle cycles per stage in the clock64 trace).  (The same
+// change made k_wgrad_tc 45 % slower - its polling loops got laid out differently -, hence opt-in per file.)
+__device__ __forceinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
+    (void)addr;
+    (void)parity;
+    asm volatile("trap;");
+}
+#else
 static __device__ __noinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
     printf("gapart_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", (int)blockIdx.x,
            (int)threadIdx.x, addr, parity);
     __trap();
 }
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
     uint32_t addr = smem_u32(bar);
     uint32_t ok = 0, polls = 0;
@@ -174,3 +186,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
         : "memory");
 }
 
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}

@@ -321,10 +321,10 @@ class SparseUNetEngine:
         tc_f = eng.use_tc and bool(C.gp_conv_tc_supported(Cin, Cout, K, x.ld, y.ld))
         tc_b = eng.use_tc and bool(C.gp_conv_tc_supported(Cout, Cin, K, y.ld, x.ld))
         tc_w = eng.use_tc and x.ptr % 16 == 0 and bool(C.gp_conv_wgrad_tc_supported(Cin, Cout, K, x.ld, y.ld, Cin, 1))
-        # 27-tap weight gradient with MN-major operands (no transpose role): dense rows + the level's tile tables.
-        # Opt-in (GAPART_WGRAD_WIN=1): measured 112 us vs k_wgrad_tc's 70 us at level 0 (gpurun_out r2_bench_cfg3_m)
+        # 27-tap weight gradient with the gathered operand in TMEM (conv_wgrad_win.cu: no transpose pass; needs dense rows
+        # + the level's tile tables): 51 us vs k_wgrad_tc's 96 us on the level-0 layer.  GAPART_WGRAD_WIN=0 switches it off
         win_w = (eng.use_tc and kind == "subm3" and x.ld == Cin and x.ptr % 16 == 0 and
-                 os.environ.get("GAPART_WGRAD_WIN", "0") == "1" and bool(C.gp_conv_wgrad_win_supported(Cin, Cout)))
+                 os.environ.get("GAPART_WGRAD_WIN", "1") != "0" and bool(C.gp_conv_wgrad_win_supported(Cin, Cout)))
         # weight images of the tensor-core convs live for the whole step: packed once by pack_weights()
         pk_f = eng._add_pack(w, Cin, 1, K * Cin, 0, K, Cin, Cout) if tc_f else None
         pk_b = eng._add_pack(w, Cin, K * Cin, 1, flip_b, K, Cout, Cin) if tc_b else None

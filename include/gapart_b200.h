@@ -193,6 +193,8 @@ int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, in
  * dW[co * w_sco + k * Cin + ci] += sum_r X[nbr_k(r), ci] * dY[r, co].  Replaces gp_conv_wgrad_tc for the shapes
  * gp_conv_wgrad_win_supported() accepts (Cin in {16, 32, 64}). */
 int gp_conv_wgrad_win_supported(int Cin, int Cout);
+/* perf tooling: clock64 trace of CTA 0 into ts[12][256] (device memory; NULL switches it off) */
+int gp_conv_wgrad_win_set_trace(long long* ts);
 int gp_conv_wgrad_win(const float* X, int Cin, const float* dY, int ldy, int Cout, const int* tile_win, const int* tile_tbl,
                       const int* d_n_out, int max_out, float* dW, long long w_sco, void* stream);
 int gp_conv_wgrad_tc_supported(int Cin, int Cout, int K, int ldx, int ldy, long long w_sk, long long w_sci);

@@ -260,10 +260,11 @@ def test_tc_window_variant_matches(cuda, cin, cout, shuffled):
 
 
 @pytest.mark.parametrize("cin,cout,shuffled", [(16, 16, False), (16, 32, False), (32, 32, False), (64, 64, False), (16, 16, True),
-                                               (32, 16, False), (16, 64, False)])
+                                               (32, 16, False), (16, 64, False), (48, 48, False), (64, 32, False), (96, 48, False),
+                                               (48, 48, True), (20, 16, False)])
 def test_wgrad_win_matches_fp64(cuda, cin, cout, shuffled):
-    """gp_conv_wgrad_win (MN-major tcgen05 operands, SWIZZLE_128B_BASE32B; gathered rows and dY rows go into shared memory
-    as they are - no transpose) vs fp64: rows in lexicographic order, rows in SHUFFLED order (neighbour ranges far longer
+    """gp_conv_wgrad_win (A operand gathered straight into TMEM - one (tap, channel) per lane -, dY rows as an MN-major
+    SWIZZLE_128B_BASE32B shared-memory operand; no transpose pass) vs fp64: rows in lexicographic order, rows in SHUFFLED order (neighbour ranges far longer
     than the window buffer: the global fall-back), a device-side row count short of the bound, accumulation into dW."""
     from gapartnet_b200._lib import C
 
