@@ -362,6 +362,21 @@ int gp_pn2_three_interpolate(int b, int c, int m, int n, const float* points, co
 int gp_pn2_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx,
                                   const float* weight, float* grad_points, void* stream);
 
+/* ---- batched part-pose fitting (csrc/pose.cu) --------------------------------------------------------------------------
+ * Replaces the per-proposal numpy estimate_pose_from_npcs(xyz, npcs) of gapartnet/misc/pose_fitting.py:121-147 (callers
+ * network/model.py:975, structure/utils.py:185): RANSAC over 5-point Umeyama models (:54-80), final Umeyama on the
+ * inliers (:4-39), oriented box (:136-145), one CTA per proposal, fp64.
+ *   xyz, npcs          [N,3] f32, proposal p owns rows proposal_offsets[p] .. proposal_offsets[p+1]
+ *   rand_idx           [P, max_iters, 5] i32: the 5 sample indices of every iteration (numpy's randint(n, size=5), :63)
+ *   out_transform      [P,16] row-major 4x4 (:34-36), out_scale [P], out_rotation [P,9], out_translation [P,3],
+ *   out_bbox           [P,8,3] (:147), inlier_mask [N] u8 (best_inlier_idx as a mask), n_inliers [P],
+ *   status             [P] 1 = pose, 0 = none (best_inlier_ratio < 0.01, :109-110, or an empty proposal),
+ *   best_iter          [P] index of the winning RANSAC iteration (-1: none)                                              */
+int gp_pose_fit(const float* xyz, const float* npcs, const long long* proposal_offsets, int num_proposals,
+                const int* rand_idx, int max_iters, double stop_thrsh, double* out_transform, double* out_scale,
+                double* out_rotation, double* out_translation, double* out_bbox, unsigned char* inlier_mask,
+                int* n_inliers, int* status, int* best_iter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
