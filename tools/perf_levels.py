@@ -44,7 +44,8 @@ def timed(g, n=20):
 
 
 prev = None
-for d in range(1, len(bench.CHANNELS) + 1):
+depths = [int(v) for v in os.environ.get("DEPTHS", "1,2,3,4,5,6,7").split(",")]
+for d in depths:
     torch.manual_seed(23333)
     net = mirror.build_sparse_unet(sp, bench.IN_CH, bench.CHANNELS[:d], bench.BLOCK_REPEAT).to(dev)
     eng = SparseUNetEngine(net, batch=BATCH, max_points=N, spatial_shape=(SHAPE,) * 3, voxel_size=VOXEL,
@@ -62,7 +63,7 @@ for d in range(1, len(bench.CHANNELS) + 1):
     t = [timed(g) for g in gs]
     tot = sum(t)
     line = "depth %d  levels %-52s build %.3f  fwd %.3f  bwd %.3f  total %.3f" % (d, eng.level_counts(), *t, tot)
-    if prev is not None:
+    if prev is not None and len(depths) == 7:
         line += "   (+%.3f: build %+.3f fwd %+.3f bwd %+.3f)" % (tot - sum(prev), *[a - b for a, b in zip(t, prev)])
     print(line, flush=True)
     prev = t
