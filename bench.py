@@ -46,8 +46,9 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the L0 16->16 kernels from the committed `ncu --set full`
 # captures (profiles/): a capture, not a live measurement - labelled as such in the JSON line
-TRAFFIC_NCU = {"k_conv_win": 23635200.0, "k_wgrad_tc": 32341760.0,
-               "source": "ncu --set full captures: profiles/prof_conv_win_r2.metrics.txt, profiles/prof_wgrad_tc_r1.metrics.txt"}
+TRAFFIC_NCU = {"k_conv_win": 23635200.0, "k_wgrad_tc": 32341760.0, "k_wgrad_win": 32375552.0,
+               "source": "ncu --set full captures (not live): profiles/prof_conv_win_r2.metrics.txt, "
+                         "profiles/prof_wgrad_win_r2.metrics.txt, profiles/prof_wgrad_tc_r1.metrics.txt"}
 
 
 def _peaks():
@@ -384,7 +385,7 @@ def run_ours(args):
         roof["other_kernels"] = [entry(wg_name, t_wgrad)]
         if args.workload == "cfg3":      # the captures were taken on this workload's level-0 shape
             roof["traffic"] = TRAFFIC_NCU["k_conv_win"]
-            roof["other_kernels"][0]["traffic"] = TRAFFIC_NCU["k_wgrad_tc"] if "k_wgrad_tc" in wg_name else None
+            roof["other_kernels"][0]["traffic"] = TRAFFIC_NCU["k_wgrad_tc" if "k_wgrad_tc" in wg_name else "k_wgrad_win"]
             roof["traffic_source"] = TRAFFIC_NCU["source"]
         # whole-step algorithmic traffic of the backbone against the step time
         per_scene = algorithmic_bytes_per_scene([c / BATCH for c in level_rows], 1)

@@ -135,11 +135,35 @@ class _SegMaxPool(torch.autograd.Function):
     def backward(ctx, g):
         (arg,) = ctx.saved_tensors
         Cc = g.shape[1]
+        # every (segment, channel) owns ONE element of dx (segments are disjoint row ranges): a plain scatter, no atomics
+        # (index_add_ cost 327 us here); empty segments (arg = -1) write their zero into a spare slot behind the tensor
         ok = arg >= 0
-        flat = arg.clamp(min=0).long() * Cc + torch.arange(Cc, device=g.device)[None, :]
-        dx = torch.zeros(ctx.n * Cc, dtype=g.dtype, device=g.device)
-        dx.index_add_(0, flat.reshape(-1), torch.where(ok, g, torch.zeros_like(g)).reshape(-1))
-        return dx.view(ctx.n, Cc), None, None
+        flat = torch.where(ok, arg.long() * Cc + torch.arange(Cc, device=g.device)[None, :],
+                           torch.full_like(arg, ctx.n * Cc, dtype=torch.long))
+        dx = torch.zeros(ctx.n * Cc + 1, dtype=g.dtype, device=g.device)
+        dx.scatter_(0, flat.reshape(-1), torch.where(ok, g, torch.zeros_like(g)).reshape(-1))
+        return dx[:-1].view(ctx.n, Cc), None, None
+
+
+class _SegSum(torch.autograd.Function):
+    """per-proposal sums of per-point rows: x [n, C] in CSR (proposal) order, begin / end [S] -> [S, C].  The reference's
+    scatter over proposal ids (grouping_utils.py:33-37) as a segmented reduction: `index_add_` with SORTED indices
+    serialises its atomics (327 us per call on 640 k rows), gp_segmented_reduce walks each proposal's rows (fp64
+    accumulation, deterministic).  backward: a row gather by proposal id."""
+
+    @staticmethod
+    def forward(ctx, x, begin, end, pidx):
+        x = x.contiguous()
+        S, Cc = begin.numel(), x.shape[1]
+        out = torch.empty(S, Cc, dtype=torch.float32, device=x.device)
+        C.gp_segmented_reduce(_p(x), x.stride(0), Cc, _p(begin), _p(end), S, 0, _p(out), None, _stream())
+        ctx.save_for_backward(pidx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (pidx,) = ctx.saved_tensors
+        return g.index_select(0, pidx), None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -175,7 +199,7 @@ def gt_scores_static(ious, fg: float = 0.75, bg: float = 0.25):
     return torch.where(ious > fg, torch.ones_like(ious), torch.where(ious < bg, torch.zeros_like(ious), ious * k + b))
 
 
-def npcs_group_loss_static(npcs, gt, pidx, mask, mats, type_idx, max_proposals: int):
+def npcs_group_loss_static(npcs, gt, pidx, mask, mats, type_idx, max_proposals: int, begin=None, end=None):
     """compute_npcs_loss (grouping_utils.py:14-43) for one symmetry group over static shapes.
     npcs, gt [n,3]; pidx [n] proposal ids; mask [n] points of this group; mats [T, m, 3, 3] the group's symmetry types,
     type_idx [n] in [0, T) (None when T == 1).  `gt[:, None, None, :] @ mats[type]` is evaluated as ONE [n,3] x [3, T*m*3]
@@ -192,8 +216,12 @@ def npcs_group_loss_static(npcs, gt, pidx, mask, mats, type_idx, max_proposals: 
     dist2 = torch.where(mask[:, None], dist2, torch.ones_like(dist2))    # keep sqrt' finite on masked rows
     loss = torch.where(dist2 <= 0.01, 5 * dist2, torch.sqrt(dist2) - 0.05)
     loss = torch.where(mask[:, None], loss, torch.zeros_like(loss))
-    sums = torch.zeros(max_proposals, m, dtype=loss.dtype, device=loss.device).index_add_(0, pidx, loss)
-    cnt = torch.zeros(max_proposals, dtype=loss.dtype, device=loss.device).index_add_(0, pidx, mask.to(loss.dtype))
+    if begin is not None:         # rows in proposal (CSR) order: segmented sums, rows past the last proposal are masked anyway
+        sums = _SegSum.apply(loss, begin, end, pidx)
+        cnt = _SegSum.apply(mask.to(loss.dtype)[:, None], begin, end, pidx).squeeze(1)
+    else:
+        sums = torch.zeros(max_proposals, m, dtype=loss.dtype, device=loss.device).index_add_(0, pidx, loss)
+        cnt = torch.zeros(max_proposals, dtype=loss.dtype, device=loss.device).index_add_(0, pidx, mask.to(loss.dtype))
     present = cnt > 0
     per_prop = (sums / cnt.clamp(min=1.0)[:, None]).min(dim=-1)[0]
     return torch.where(present, per_prop, torch.zeros_like(per_prop)).sum() / present.to(loss.dtype).sum().clamp(min=1.0)
@@ -369,9 +397,9 @@ class FusedTrainStep:
         npcs = npcs_logits.view(2 * N, -1, 3).gather(1, cls[:, None, None].expand(2 * N, 1, 3)).squeeze(1)
         sym = net.symmetry_indices[prop_sem_preds.clamp(min=0, max=net.symmetry_indices.numel() - 1)]
         pidx = st.proposal_indices[:2 * N].long().clamp(max=maxP - 1)
-        loss_npcs = npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym < 3), net.symmetry_matrix_1, sym, maxP)
-        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 3), net.symmetry_matrix_2, None, maxP)
-        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 4), net.symmetry_matrix_3, None, maxP)
+        loss_npcs = npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym < 3), net.symmetry_matrix_1, sym, maxP, begin, end)
+        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 3), net.symmetry_matrix_2, None, maxP, begin, end)
+        loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 4), net.symmetry_matrix_3, None, maxP, begin, end)
 
         loss = loss_sem + loss_dist + loss_dir + loss_score + loss_npcs
         loss.backward()

@@ -63,6 +63,8 @@ if os.environ.get("EXPS"):
             print("L%d %d->%d exp %d (1 no lo store, 2 one idx load, 4 no data loads): %.1f us" % (L, cin, cout, exp, t_win), flush=True)
     os.environ["GAPART_WW_EXP"] = "0"
     shapes = []
+if os.environ.get("ONLY"):
+    shapes = shapes[: int(os.environ["ONLY"])]
 for L, cin, cout in shapes:
     M = eng.max_rows[L]
     x = torch.randn(M, cin, device=dev)
