@@ -452,10 +452,14 @@ __global__ void __launch_bounds__(32 * CG_WARPS) k_cg_cluster_merge(const float4
     // cap-th smallest hit - 4.9 ms: most queries stay below the cap and must see every candidate anyway.)
     constexpr int WSUB = 4, WLEN = 32 * WSUB;
     int wb = cur;
-    unsigned mask[WSUB] = {0, 0, 0, 0};
+    // the window's hit mask as two 64-bit words: consuming the lowest hit and finding the next one are a handful of
+    // instructions (the merge loop below runs once per HIT: 300 rounds per query of the shifted-coordinate clustering, where
+    // every query is truncated - ncu: 16 k warp instructions per query with four 32-bit words scanned per round)
+    unsigned long long mlo = 0, mhi = 0;
     auto test_window = [&](int l) {          // (warp-uniform l) test the 128 entries at lane l's window position
         const int bl = __shfl_sync(0xffffffffu, wb, l), el = __shfl_sync(0xffffffffu, end, l);
         int k[WSUB];
+        unsigned bal[WSUB];
 #pragma unroll
         for (int j = 0; j < WSUB; ++j) {
             const int pos = bl + 32 * j + lane;
@@ -464,11 +468,14 @@ __global__ void __launch_bounds__(32 * CG_WARPS) k_cg_cluster_merge(const float4
 #pragma unroll
         for (int j = 0; j < WSUB; ++j) {
             const bool hit = k[j] >= 0 && cg_hit(pts, k[j], c, lab, use_labels, radius2);
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (lane == l) mask[j] = bal;
+            bal[j] = __ballot_sync(0xffffffffu, hit);
+        }
+        if (lane == l) {
+            mlo = (unsigned long long)bal[0] | ((unsigned long long)bal[1] << 32);
+            mhi = (unsigned long long)bal[2] | ((unsigned long long)bal[3] << 32);
         }
     };
-    auto empty = [&]() { return (mask[0] | mask[1] | mask[2] | mask[3]) == 0; };
+    auto empty = [&]() { return (mlo | mhi) == 0ull; };
 #pragma unroll 1
     for (int l = 0; l < 27; ++l)
         if (__shfl_sync(0xffffffffu, end - wb, l) > 0) test_window(l);
@@ -486,9 +493,8 @@ __global__ void __launch_bounds__(32 * CG_WARPS) k_cg_cluster_merge(const float4
     const int lim = cap < CG_HSLOTS * 32 ? cap : CG_HSLOTS * 32;
     int cnt = 0;
     auto first_hit = [&]() -> int {          // index of the lowest unconsumed hit of the window, INF if none
-#pragma unroll
-        for (int j = 0; j < WSUB; ++j)
-            if (mask[j]) return __ldg(order + wb + 32 * j + __ffs(mask[j]) - 1);
+        if (mlo) return __ldg(order + wb + __ffsll((long long)mlo) - 1);
+        if (mhi) return __ldg(order + wb + 64 + __ffsll((long long)mhi) - 1);
         return INF;
     };
     int head = first_hit();
@@ -498,10 +504,8 @@ __global__ void __launch_bounds__(32 * CG_WARPS) k_cg_cluster_merge(const float4
         const bool mine = head == m;             // exactly one lane: point indices are unique
         if (mine) {
             strip[cnt] = m;
-            bool done = false;                   // consume the lowest hit of the window
-#pragma unroll
-            for (int j = 0; j < WSUB; ++j)
-                if (!done && mask[j]) { mask[j] &= mask[j] - 1; done = true; }
+            if (mlo) mlo &= mlo - 1;             // consume the lowest hit of the window
+            else mhi &= mhi - 1;
         }
         ++cnt;
         if (__any_sync(0xffffffffu, mine && empty() && wb + WLEN < end)) settle();
