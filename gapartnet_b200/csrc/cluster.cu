@@ -211,22 +211,40 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 __global__ void k_cg_min(const float4* __restrict__ pts, int n, const int* __restrict__ d_n, unsigned* __restrict__ mn) {
     n = gp_rows(d_n, n);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned x = 0xffffffffu, y = 0xffffffffu, z = 0xffffffffu;
+    unsigned x = 0xffffffffu, y = 0xffffffffu, z = 0xffffffffu, X = 0u, Y = 0u, Z = 0u;
     if (i < n) {
         float4 p = pts[i];
-        x = f2ord(p.x); y = f2ord(p.y); z = f2ord(p.z);
+        x = X = f2ord(p.x); y = Y = f2ord(p.y); z = Z = f2ord(p.z);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         x = min(x, __shfl_xor_sync(0xffffffffu, x, o));
         y = min(y, __shfl_xor_sync(0xffffffffu, y, o));
         z = min(z, __shfl_xor_sync(0xffffffffu, z, o));
+        X = max(X, __shfl_xor_sync(0xffffffffu, X, o));
+        Y = max(Y, __shfl_xor_sync(0xffffffffu, Y, o));
+        Z = max(Z, __shfl_xor_sync(0xffffffffu, Z, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMin(mn + 0, x); atomicMin(mn + 1, y); atomicMin(mn + 2, z);
+        if (i - (int)(threadIdx.x & 31) < n) { atomicMax(mn + 3, X); atomicMax(mn + 4, Y); atomicMax(mn + 5, Z); }
     }
 }
-__device__ __forceinline__ int3 cg_cell(float4 p, const unsigned* mn, float inv_cell) {
+// Cell size: 0.1 % larger than the radius (two points closer than the radius are at most one cell apart per axis even after
+// the fp32 rounding of (x - min) / cell), but never so small that the CG cells per axis do not span the data: coordinates
+// beyond the grid used to be CLAMPED into the boundary cells, and the shifted-coordinate clustering of an untrained offset
+// head (xyz + garbage offsets several units long) put most points there - 16 k candidates per query (ncu: 5.07 ms per
+// call).  mn[6] = 1 / cell as float bits.
+__global__ void k_cg_cellsize(unsigned* __restrict__ mn, float radius) {
+    float ext = 0.f;
+    for (int a = 0; a < 3; ++a)
+        if (mn[3 + a] >= mn[a]) ext = fmaxf(ext, ord2f(mn[3 + a]) - ord2f(mn[a]));
+    float cell = radius * 1.001f;
+    if (ext == ext && ext < 3.0e38f) cell = fmaxf(cell, ext * 1.0001f / (float)CG);
+    mn[6] = __float_as_uint(1.0f / cell);
+}
+__device__ __forceinline__ int3 cg_cell(float4 p, const unsigned* mn, float) {
+    const float inv_cell = __uint_as_float(__ldg(mn + 6));
     int3 c;
     c.x = min(max((int)floorf((p.x - ord2f(mn[0])) * inv_cell), 0), CG - 1);
     c.y = min(max((int)floorf((p.y - ord2f(mn[1])) * inv_cell), 0), CG - 1);
@@ -580,9 +598,7 @@ int cg_cluster_packed(const float4* pts4, const int* batch_indices, const int* b
     unsigned* mn = reinterpret_cast<unsigned*>(starts + (cells + 1));
     void* cub_tmp = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(mn + 8) + 255) & ~(uintptr_t)255);
     const int g = gp_cdiv(N, 256);
-    // cells 0.1 % larger than the radius: two points closer than the radius are at most one cell apart per axis
-    // even after the fp32 rounding of (x - min) / cell
-    const float inv_cell = 1.0f / (radius * 1.001f);
+    const float inv_cell = 0.f;      // (unused: the kernels read 1 / cell from mn[6], k_cg_cellsize)
     static int merge_enabled = -1;
     if (merge_enabled < 0) {
         const char* e = getenv("GAPART_CLUSTER_MERGE");
@@ -590,8 +606,10 @@ int cg_cluster_packed(const float4* pts4, const int* batch_indices, const int* b
     }
     k_iota<<<g, 256, 0, stream>>>(cc_labels, N);
     GP_CUDA(cudaMemsetAsync(mn, 0xff, 3 * sizeof(unsigned), stream));
+    GP_CUDA(cudaMemsetAsync(mn + 3, 0, 3 * sizeof(unsigned), stream));
     GP_CUDA(cudaMemsetAsync(counts, 0, (size_t)(cells + 1) * sizeof(int), stream));
     k_cg_min<<<g, 256, 0, stream>>>(pts4, N, d_n, mn);
+    k_cg_cellsize<<<1, 1, 0, stream>>>(mn, radius);
     if (merge_enabled && num_samples <= CG_HSLOTS * 32) {
         // stable sort of (cell key, point index): every cell's list in ascending point index
         int key_bits = 1;
@@ -612,7 +630,7 @@ int cg_cluster_packed(const float4* pts4, const int* batch_indices, const int* b
                                                                           cc_labels);
     }
     k_ccl_flatten<<<g, 256, 0, stream>>>(cc_labels, N);
-    gp_note_launch(7);
+    gp_note_launch(8);
     GP_LAUNCH_CHECK();
     return GP_OK;
 }
