@@ -25,12 +25,15 @@
 //          registers.  The price is a fixed permutation of the 32 K positions inside a chunk, which
 //          k_pack_weights applies to the weight images (tc_kperm).
 //
-// Warp roles (704 threads, 1 CTA/SM, persistent over work items = (128-row tile, K split part)):
-//   warps 0-3    epilogue : tcgen05.ld accumulator -> global rows (+BN sum/sumsq), double-buffered TMEM
-//   warps 4-19   feeders  : 4 groups x 4 TMEM quadrants; group g feeds chunks n == g (mod 4) into A stage g
-//   warp  20     MMA      : elected lane issues 12 tcgen05.mma.kind::tf32 per chunk (A from TMEM, B smem)
-//   warp  21     loader   : weight images (cp.async.bulk per chunk) + neighbour-index tiles of the next
-//                           work item (Ktaps bulk copies), completion on mbarriers
+// Warp roles (template parameter G = feeder groups: 32 * (4 + 4 G + 2) threads - 448 for the generic G = 2 instance, 576
+// for the G = 3 window instance -, 1 CTA/SM, persistent over work items = (128-row tile, K split part)):
+//   warps 0-3        epilogue : tcgen05.ld accumulator -> global rows (+BN sum/sumsq), double-buffered TMEM
+//   warps 4..4+4G-1  feeders  : G groups x 4 TMEM quadrants; group g feeds chunks n == g (mod G) into its A stages
+//   warp  4+4G       MMA      : one elected thread issues the tcgen05.mma.kind::tf32 of a chunk (A from TMEM, B smem)
+//   warp  5+4G       loader   : weight images (cp.async.bulk per chunk) + neighbour-index tiles of the next
+//                               work item (Ktaps bulk copies), completion on mbarriers
+// (The 27-tap SubM convs of levels 0-2 run on the specialised k_conv_win, conv_win.cu; this kernel keeps the 1x1, strided,
+// inverse and deep-level convs and the split-K path.)
 // Lessons kept from v1/v2: mbarrier hops cost ~400 cycles (every role runs ahead on its own counters);
 // a bare try_wait loop burnt 58 % of all issued instructions (nanosleep back-off in mbar_wait);
 // 64-bit division and lane-divergent MMA issue (R2UR waterfall) each cost >1k cycles per chunk;

@@ -186,17 +186,19 @@ int gp_conv_wgrad(const float* X, int ldx, int Cin, const float* dY, int ldy, in
                   const int* nbr, int tbl_stride, int K, const int* d_n_out, int max_out, float* dW,
                   long long w_sk, long long w_sci, long long w_sco, int flip_k, void* stream);
 
-/* gp_conv_wgrad on the tcgen05 tensor cores (3xTF32; csrc/conv_wgrad_tc.cu). Needs KRSC weight strides
- * (w_sci == 1, w_sk == Cin), Cin % 4 == 0, Cout <= 128; rows_hint as in gp_conv_tc_fwd. */
-/* Weight gradient of a 27-tap SubMConv3d with MN-major tcgen05 operands (conv_wgrad_win.cu): the table is given as
- * gp_tile_windows' window table + tile-major table, X has dense rows (ld = Cin).
- * dW[co * w_sco + k * Cin + ci] += sum_r X[nbr_k(r), ci] * dY[r, co].  Replaces gp_conv_wgrad_tc for the shapes
- * gp_conv_wgrad_win_supported() accepts (Cin in {16, 32, 64}). */
+/* Weight gradient of a 27-tap SubMConv3d with the gathered operand written straight into tensor memory (conv_wgrad_win.cu:
+ * lane = (tap, ci), column = row; dY as an MN-major shared-memory operand; 3xTF32).  The table is given as
+ * gp_tile_windows' window table + tile-major table, X has dense rows (ld = Cin), KRSC weight-gradient layout:
+ *   dW[co * w_sco + k * Cin + ci] += sum_r X[nbr_k(r), ci] * dY[r, co].
+ * gp_conv_wgrad_win_supported(): Cin % 4 == 0, 16 <= Cin <= 128, Cout % 16 == 0, Cout <= 128 and a shared-memory window of
+ * at least 256 input rows next to the dY tiles (e.g. 16..64 -> 16..48 channels); other shapes use gp_conv_wgrad_tc. */
 int gp_conv_wgrad_win_supported(int Cin, int Cout);
 /* perf tooling: clock64 trace of CTA 0 into ts[12][256] (device memory; NULL switches it off) */
 int gp_conv_wgrad_win_set_trace(long long* ts);
 int gp_conv_wgrad_win(const float* X, int Cin, const float* dY, int ldy, int Cout, const int* tile_win, const int* tile_tbl,
                       const int* d_n_out, int max_out, float* dW, long long w_sco, void* stream);
+/* gp_conv_wgrad on the tcgen05 tensor cores (3xTF32; csrc/conv_wgrad_tc.cu). Needs KRSC weight strides
+ * (w_sci == 1, w_sk == Cin), Cin % 4 == 0, Cout <= 128; rows_hint as in gp_conv_tc_fwd. */
 int gp_conv_wgrad_tc_supported(int Cin, int Cout, int K, int ldx, int ldy, long long w_sk, long long w_sci);
 int gp_conv_wgrad_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, const int* nbr,
                      int tbl_stride, int K, const int* d_n_out, int max_out, float* dW, long long w_sk,
