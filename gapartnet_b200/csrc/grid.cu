@@ -299,8 +299,9 @@ extern "C" int gp_scene_range(const float* xyz, int xyz_stride, const int64_t* b
                               void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_CHECK_ARG(batch > 0 && xyz_stride >= 3, "gp_scene_range: bad batch/stride");
-    k_scene_range<<<batch, 256, 0, stream>>>(xyz, xyz_stride, (const long long*)batch_offsets, pad,
-                                             range_min, range_max);
+    // one CTA per scene, on the critical path in front of the voxeliser: 1024 threads (26 us with 256 at 16 x 20 k points)
+    k_scene_range<<<batch, 1024, 0, stream>>>(xyz, xyz_stride, (const long long*)batch_offsets, pad,
+                                              range_min, range_max);
     gp_note_launch(1);
     GP_LAUNCH_CHECK();
     return GP_OK;
