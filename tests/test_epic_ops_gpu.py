@@ -97,6 +97,27 @@ def test_segmented_reduce(cuda, mode):
         np.testing.assert_array_equal(out.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("mode,C", [("sum", 12), ("sum", 1), ("max", 16), ("min", 5), ("sum", 7)])
+def test_segmented_reduce_many_short_segments(cuda, mode, C):
+    """the warp-per-segment kernels (S >= 4096, C <= 16: the per-proposal sums / max-pool of the train step): short
+    segments, empties in between, values with ties (argmax = first maximum)"""
+    g = np.random.default_rng(7)
+    S = 6000
+    lens = g.integers(0, 70, S)
+    lens[g.random(S) < 0.1] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    x = np.round(g.normal(size=(int(off[-1]) + 5, C)) * 4).astype(np.float32) / 4          # ties on purpose
+    begin, end = off[:-1].copy(), off[1:].copy()
+    xt, bt, et = torch.from_numpy(x).to(cuda), torch.from_numpy(begin).to(cuda), torch.from_numpy(end).to(cuda)
+    ref, rarg = oc.segmented_reduce(x, begin, end, mode)
+    if mode == "max":
+        out, arg = reduce.segmented_maxpool(xt, bt, et)
+        np.testing.assert_array_equal(arg.cpu().numpy(), rarg)
+    else:
+        out = reduce.segmented_reduce(xt, bt, et, mode=mode)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)        # quarter-integers: sums are exact
+
+
 def test_segmented_maxpool_forward_backward(cuda):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(3000, 16, generator=g)
