@@ -736,14 +736,30 @@ __global__ void __launch_bounds__(256) k_seg_reduce_warp(const float* __restrict
         acc[j] = MODE == 0 ? 0.0 : (MODE == 1 ? (double)FLT_MAX : -(double)FLT_MAX);
         arg[j] = 0x7fffffff;
     }
-    for (int r = b + lane; r < e; r += 32) {
-        const float* row = x + (size_t)r * ldx;
+    // 4 rows per lane and trip with all loads issued first: the untrained network's largest proposals hold thousands of
+    // rows and ONE warp walks them - the kernel's time is that warp's chain of load latencies (304 us for the max-pool of
+    // a cfg4 step before the unroll, profiles/launches_r2_cfg4_step.csv)
+    for (int r0 = b + lane; r0 < e; r0 += 128) {
+        float v[4][CH];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const double v = j < C ? (double)__ldg(row + j) : 0.0;
-            if (MODE == 0) acc[j] += v;
-            else if (MODE == 1) acc[j] = fmin(acc[j], v);
-            else if (v > acc[j] || arg[j] == 0x7fffffff) { acc[j] = v; arg[j] = r; }
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + 32 * u;
+            const float* row = x + (size_t)(r < e ? r : r0) * ldx;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[u][j] = j < C ? __ldg(row + j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + 32 * u;
+            if (r < e) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const double w = (double)v[u][j];
+                    if (MODE == 0) acc[j] += w;
+                    else if (MODE == 1) acc[j] = fmin(acc[j], w);
+                    else if (w > acc[j] || arg[j] == 0x7fffffff) { acc[j] = w; arg[j] = r; }
+                }
+            }
         }
     }
 #pragma unroll

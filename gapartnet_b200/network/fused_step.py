@@ -166,6 +166,31 @@ class _SegSum(torch.autograd.Function):
         return g.index_select(0, pidx), None, None, None
 
 
+class _NpcsHeadLoss(torch.autograd.Function):
+    """npcs_head + loss_proposal_npcs (model.py:387-462, grouping_utils.py:14-43) on the per proposal-point features of the
+    NPCS U-Net: gp_npcs_loss_fwd / gp_npcs_loss_bwd (csrc/npcs_loss.cu).  Only the 3 head outputs of a row's predicted class
+    are ever computed, nothing of size [2N, m, 3] exists; `npcs_group_loss_static` below is the torch formulation it
+    replaced (kept as the test's reference)."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, step, sem_preds):
+        loss = torch.empty((), dtype=torch.float32, device=feats.device)
+        args = step._npcs_args(feats, weight, bias, sem_preds)
+        C.gp_npcs_loss_fwd(*args, _p(step._npcs_ws), _p(loss), _stream())
+        ctx.args, ctx.step = args, step
+        ctx.keep = (feats, weight, bias, sem_preds)           # the kernels of the backward read these buffers again
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, weight, bias, _ = ctx.keep
+        g = g.contiguous().float()
+        dF = torch.empty_like(feats)
+        dW, db = torch.zeros_like(weight), torch.zeros_like(bias)
+        C.gp_npcs_loss_bwd(*ctx.args, _p(ctx.step._npcs_ws), _p(g), _p(dF), dF.stride(0), _p(dW), _p(db), _stream())
+        return dF, dW, db, None, None
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # losses over static shapes (masks instead of boolean indexing); same arithmetic as network/losses.py + model.py
 # ---------------------------------------------------------------------------------------------------------------------
@@ -303,6 +328,24 @@ class FusedTrainStep:
         self.use_graph = use_graph
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._warm = 0
+        # fused NPCS head + loss (csrc/npcs_loss.cu); GAPART_NPCS_FUSED=0 runs the torch formulation instead
+        self.fused_npcs = os.environ.get("GAPART_NPCS_FUSED", "1") != "0" and net.npcs_head.in_features == 16 \
+            and net.npcs_head.out_features <= 48
+        self._npcs_ws = torch.zeros(int(C.gp_npcs_loss_ws_bytes(self.maxP)) // 8 + 1, dtype=torch.float64, device=dev)
+        self._sym_mats = [m.contiguous() for m in (net.symmetry_matrix_1, net.symmetry_matrix_2, net.symmetry_matrix_3)]
+        if self.fused_npcs and [tuple(m.shape) for m in self._sym_mats] != [(3, 2, 3, 3), (1, 12, 3, 3), (1, 24, 3, 3)]:
+            self.fused_npcs = False
+
+    def _npcs_args(self, feats, weight, bias, sem_preds):
+        """the argument list gp_npcs_loss_fwd / _bwd share (everything up to the workspace pointer)"""
+        net, st = self.net, self.stage
+        if not (feats.is_contiguous() and weight.is_contiguous() and sem_preds.dtype == torch.int64):
+            raise GapartError("fused NPCS loss: contiguous features / weights and int64 predictions expected")
+        sym = net.symmetry_indices
+        m1, m2, m3 = self._sym_mats
+        return (_p(feats), feats.stride(0), feats.shape[1], _p(weight), _p(bias), weight.shape[0], _p(st.prop_point),
+                _p(st.proposal_indices), 2 * self.N, _p(sem_preds), _p(self.sem_labels), _p(self.gt_npcs), _p(sym),
+                sym.numel(), _p(m1), _p(m2), _p(m3), _p(st.counts), st.NP, st.P, self.maxP)
 
     # ------------------------------------------------------------------------------------------------------------------
     def load(self, batch: PointBatch, rand: Optional[torch.Tensor] = None):
@@ -366,12 +409,12 @@ class FusedTrainStep:
         ppl = pp.long()
         pt_mask = self._arange2N < np_t                       # proposal points that exist
         pr_mask = self._arangeP < p_t                         # proposals that exist
-        pfeat = _GatherRows.apply(pc_feature, pp)
+        # rows beyond the count hold stale indices (mostly 0): as gather indices they are harmless, but the backward's
+        # scatter-add serialised 260 k rows of atomics on row 0 (429 us, profiles/launches_r2_cfg4_step.csv): -1 = skip
+        pfeat = _GatherRows.apply(pc_feature, torch.where(pt_mask, pp, torch.full_like(pp, -1)))
         vox = _ProposalVoxelize.apply(pfeat, st, self.score_engine)
         off32 = st.proposal_offsets.int()
         begin, end = off32[:-1], off32[1:]
-        prop_sem_preds = sem_preds[ppl]
-        prop_sem_labels = sem_labels[ppl]
 
         # ---- ScoreNet (model.py:348-385, :540-562) ---------------------------------------------------------------------
         score_feats = _ProposalUNet.apply(vox, self.score_engine)
@@ -390,6 +433,23 @@ class FusedTrainStep:
 
         # ---- NPCS (model.py:387-462) -------------------------------------------------------------------------------------
         npcs_feats = _ProposalUNet.apply(vox, self.npcs_engine)
+        if self.fused_npcs:
+            loss_npcs = _NpcsHeadLoss.apply(npcs_feats, net.npcs_head.weight, net.npcs_head.bias, self, sem_preds)
+        else:
+            loss_npcs = self._npcs_loss_torch(npcs_feats, ppl, pt_mask, sem_preds, begin, end)
+
+        loss = loss_sem + loss_dist + loss_dir + loss_score + loss_npcs
+        loss.backward()
+        self.losses = dict(loss=loss.detach(), loss_sem_seg=loss_sem.detach(), loss_offset_dist=loss_dist.detach(),
+                           loss_offset_dir=loss_dir.detach(), loss_prop_score=loss_score.detach(),
+                           loss_prop_npcs=loss_npcs.detach(), all_accu=all_accu, pixel_accu=pixel_accu)
+        self.debug = dict(sem_logits=sem_logits.detach(), offsets=offsets.detach(), sem_preds=sem_preds,
+                          score_logits_all=score_logits_all.detach(), ious=ious, pc_feature=pc_feature.detach())
+
+    def _npcs_loss_torch(self, npcs_feats, ppl, pt_mask, sem_preds, begin, end):
+        """the static-shape torch formulation of npcs_head + loss_proposal_npcs (reference of the fused kernels)"""
+        net, st, N, maxP = self.net, self.stage, self.N, self.maxP
+        prop_sem_preds, prop_sem_labels = sem_preds[ppl], self.sem_labels[ppl]
         npcs_logits = net.npcs_head(npcs_feats)                                # head and row gather commute
         gt = self.gt_npcs[ppl]
         nvalid = pt_mask & (prop_sem_preds == prop_sem_labels) & (gt != 0).any(dim=-1)
@@ -400,14 +460,7 @@ class FusedTrainStep:
         loss_npcs = npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym < 3), net.symmetry_matrix_1, sym, maxP, begin, end)
         loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 3), net.symmetry_matrix_2, None, maxP, begin, end)
         loss_npcs = loss_npcs + npcs_group_loss_static(npcs, gt, pidx, nvalid & (sym == 4), net.symmetry_matrix_3, None, maxP, begin, end)
-
-        loss = loss_sem + loss_dist + loss_dir + loss_score + loss_npcs
-        loss.backward()
-        self.losses = dict(loss=loss.detach(), loss_sem_seg=loss_sem.detach(), loss_offset_dist=loss_dist.detach(),
-                           loss_offset_dir=loss_dir.detach(), loss_prop_score=loss_score.detach(),
-                           loss_prop_npcs=loss_npcs.detach(), all_accu=all_accu, pixel_accu=pixel_accu)
-        self.debug = dict(sem_logits=sem_logits.detach(), offsets=offsets.detach(), sem_preds=sem_preds,
-                          score_logits_all=score_logits_all.detach(), ious=ious, pc_feature=pc_feature.detach())
+        return loss_npcs
 
     def optimizer_step(self):
         """Adam (torch.optim.Adam defaults: configure_optimizers, model.py:1051-1055) over the flat arenas, one launch;

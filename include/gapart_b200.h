@@ -261,6 +261,31 @@ int gp_linear_ce(const float* F, int ldf, int C, const int64_t* labels, int N, c
                  long long ignore_index, float* logits_out, int ldl, float* dF, int lddf, float* dW, float* db,
                  double* loss, int* d_count_ws, void* stream);
 
+/* NPCS head + symmetry-aware NPCS loss over the proposal points (GAPartNet.forward_proposal_npcs / loss_proposal_npcs,
+ * gapartnet/network/model.py:387-462; compute_npcs_loss, gapartnet/network/grouping_utils.py:14-43), static shapes:
+ *   F [cap_rows, C = 16] per proposal-point features of the NPCS U-Net, rows in proposal (CSR) order; W [K,16], bias [K]
+ *   = npcs_head (K = 3 * (part classes - 1)); prop_point[r] = point of row r, proposal_indices[r] = its proposal;
+ *   sem_preds / sem_labels [N] int64 and gt_npcs [N,3] are indexed by point; symmetry_indices [n_sym] int64 (class ->
+ *   symmetry type 0..4); mats1 [3,2,3,3], mats2 [12,3,3], mats3 [24,3,3] = misc/info.py get_symmetry_matrix();
+ *   live rows = d_counts[np_slot], live proposals = d_counts[p_slot] (device ints, bounded by cap_rows / max_proposals).
+ * A row counts iff sem_pred == sem_label and gt_npcs != 0; its prediction is the 3 head outputs of class sem_pred - 1.
+ * fwd: *loss (device float) = sum over the three symmetry groups of mean_proposals min_m mean_rows l(|pred - gt M_m - .5|^2);
+ *      ws (gp_npcs_loss_ws_bytes, 8-byte aligned) keeps counts / argmin for the backward.
+ * bwd: dF [cap_rows,16] = *d_loss * d loss / d F (every row written, zeros for rows that do not count); dW [K,16] / db [K]
+ *      (optional) are ACCUMULATED into. */
+long long gp_npcs_loss_ws_bytes(int max_proposals);
+int gp_npcs_loss_fwd(const float* F, int ldf, int C, const float* W, const float* bias, int K, const int* prop_point,
+                     const int* proposal_indices, int cap_rows, const int64_t* sem_preds, const int64_t* sem_labels,
+                     const float* gt_npcs, const int64_t* symmetry_indices, int n_sym, const float* mats1,
+                     const float* mats2, const float* mats3, const int* d_counts, int np_slot, int p_slot,
+                     int max_proposals, void* ws, float* loss, void* stream);
+int gp_npcs_loss_bwd(const float* F, int ldf, int C, const float* W, const float* bias, int K, const int* prop_point,
+                     const int* proposal_indices, int cap_rows, const int64_t* sem_preds, const int64_t* sem_labels,
+                     const float* gt_npcs, const int64_t* symmetry_indices, int n_sym, const float* mats1,
+                     const float* mats2, const float* mats3, const int* d_counts, int np_slot, int p_slot,
+                     int max_proposals, const void* ws, const float* d_loss, float* dF, int lddf, float* dW, float* db,
+                     void* stream);
+
 /* ---- epic_ops: proposal clustering and scoring ------------------------------------------------ */
 /* epic_ops.ball_query.ball_query(points, query, batch_indices, batch_offsets, radius, num_samples,
  * point_labels=, query_labels=) -> (indices [Q,num_samples] i32, num_points_per_query [Q] i32)

@@ -302,3 +302,55 @@ def test_wgrad_win_matches_fp64(cuda, cin, cout, shuffled):
         ok = idx >= 0
         ref[:, k, :] += dy[:n][ok].double().t() @ x[idx[ok]].double()
     assert rel_err(dw, ref) < 2e-5
+
+
+def test_split_k_grid_counter_under_sm_contention(cuda):
+    """The split-K launches clear their output rows in-kernel and meet on a grid counter (zero_sync): that needs every CTA
+    of the launch to become resident eventually.  Force the contention the train step can produce - two split-K convs on
+    two streams (each asks for one CTA per SM and nearly the whole shared memory) next to a long cuBLAS GEMM on a third -
+    for 60 rounds: no watchdog trap, results equal to the serial launches (fp32 red.global order differs: 1e-5), counters
+    re-armed after every launch."""
+    from gapartnet_b200._lib import C
+
+    t = _table(cuda, n=700, batch=1)
+    M = t["M"]
+    assert M < 128 * 8                                   # a handful of row tiles: the K axis is split over the SMs
+    cin = cout = 112
+    g = torch.Generator(device="cpu").manual_seed(11)
+    xs = [torch.randn(M, cin, generator=g).to(cuda) for _ in range(2)]
+    w = (torch.randn(cout, 27, cin, generator=g) * 0.05).to(cuda)
+    d_n = torch.tensor([M], dtype=torch.int32, device=cuda)
+    tbl = t["nbr"].contiguous()
+    ws = torch.empty(int(C.gp_conv_tc_workspace_floats(27, cin, cout)), device=cuda)
+    st0 = torch.cuda.current_stream().cuda_stream
+    ys = [torch.empty(M, cout, device=cuda) for _ in range(2)]
+    sync = [torch.zeros(2, dtype=torch.int32, device=cuda) for _ in range(2)]
+    C.gp_conv_tc_fwd(xs[0].data_ptr(), cin, cin, w.data_ptr(), cin, 1, 27 * cin, 0, tbl.data_ptr(), tbl.shape[1], 27,
+                     d_n.data_ptr(), M, ys[0].data_ptr(), cout, cout, 0, None, ws.data_ptr(), M, st0)   # packs the weights
+    serial = []
+    for i in range(2):
+        C.gp_conv_tc_run(xs[i].data_ptr(), cin, cin, ws.data_ptr(), tbl.data_ptr(), tbl.shape[1], 27, d_n.data_ptr(), M,
+                         ys[i].data_ptr(), cout, cout, 0, None, M, sync[i].data_ptr(), None, None, st0)
+        torch.cuda.synchronize()
+        serial.append(ys[i].clone())
+        assert rel_err(serial[i], _ref(xs[i], w, tbl, 27, M)) < 6e-5
+        assert sync[i].tolist() == [0, 0]
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    a = torch.randn(4096, 4096, device=cuda)
+    torch.cuda.synchronize()
+    for it in range(60):
+        with torch.cuda.stream(streams[2]):
+            b = a @ a                                    # ~70 us of all SMs
+        main = torch.cuda.current_stream()
+        for i in (it & 1, 1 - (it & 1)):                 # alternate which conv is launched first
+            ys[i].fill_(float("nan"))
+            streams[i].wait_stream(main)
+            with torch.cuda.stream(streams[i]):
+                C.gp_conv_tc_run(xs[i].data_ptr(), cin, cin, ws.data_ptr(), tbl.data_ptr(), tbl.shape[1], 27, d_n.data_ptr(),
+                                 M, ys[i].data_ptr(), cout, cout, 0, None, M, sync[i].data_ptr(), None, None,
+                                 streams[i].cuda_stream)
+        torch.cuda.synchronize()
+        for i in range(2):
+            assert rel_err(ys[i], serial[i]) < 1e-5, (it, i)
+            assert sync[i].tolist() == [0, 0]
+    del b
