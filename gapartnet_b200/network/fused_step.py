@@ -166,6 +166,41 @@ class _SegSum(torch.autograd.Function):
         return g.index_select(0, pidx), None, None, None
 
 
+class _DenseHeads(torch.autograd.Function):
+    """sem_seg_head + offset_head with loss_sem_seg / loss_offset (model.py:160-226), forward and backward in
+    gp_dense_heads_fwd_bwd (csrc/dense_heads.cu: three passes over the points instead of ~190 torch launches).
+    -> (loss_sem + loss_dist + loss_dir [differentiable], sem_preds, sem_logits, offsets, scalars[8])"""
+
+    @staticmethod
+    def forward(ctx, feat, w_sem, b_sem, w1, b1, gamma, beta, w2, b2, step):
+        net, dev, N = step.net, feat.device, feat.shape[0]
+        bn = net.offset_head[1]
+        K = w_sem.shape[0]
+        preds = torch.empty(N, dtype=torch.int64, device=dev)
+        logits = torch.empty(N, K, dtype=torch.float32, device=dev)
+        offsets = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        scalars = torch.zeros(8, dtype=torch.float32, device=dev)
+        dF = torch.empty(N, feat.shape[1], dtype=torch.float32, device=dev)
+        grads = [torch.zeros_like(p) for p in (w_sem, b_sem, w1, b1, gamma, beta, w2, b2)]
+        pts = step.engine.points
+        C.gp_dense_heads_fwd_bwd(_p(feat), feat.stride(0), feat.shape[1], N, _p(w_sem), _p(b_sem), K, _p(w1), _p(b1),
+                                 _p(gamma), _p(beta), float(bn.eps), float(bn.momentum), _p(bn.running_mean),
+                                 _p(bn.running_var), _p(w2), _p(b2), _p(step.sem_labels), int(net.ignore_sem_label),
+                                 _p(step.instance_labels), _p(step.instance_centers), _p(pts), pts.stride(0),
+                                 int(bool(net.use_sem_focal_loss)), int(bool(net.use_sem_dice_loss)), _p(step._dense_ws),
+                                 _p(preds), _p(logits), logits.stride(0), _p(offsets), _p(scalars), _p(dF), dF.stride(0),
+                                 *[_p(g) for g in grads], _stream())
+        bn.num_batches_tracked.add_(1)
+        ctx.grads = (dF, *grads)
+        loss = scalars[5].clone()
+        ctx.mark_non_differentiable(preds, logits, offsets, scalars)
+        return loss, preds, logits, offsets, scalars
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        return tuple(x * g for x in ctx.grads) + (None,)
+
+
 class _NpcsHeadLoss(torch.autograd.Function):
     """npcs_head + loss_proposal_npcs (model.py:387-462, grouping_utils.py:14-43) on the per proposal-point features of the
     NPCS U-Net: gp_npcs_loss_fwd / gp_npcs_loss_bwd (csrc/npcs_loss.cu).  Only the 3 head outputs of a row's predicted class
@@ -328,6 +363,14 @@ class FusedTrainStep:
         self.use_graph = use_graph
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._warm = 0
+        # fused dense heads + losses (csrc/dense_heads.cu); GAPART_DENSE_FUSED=0 runs the torch formulation instead
+        oh = net.offset_head
+        self.fused_dense = os.environ.get("GAPART_DENSE_FUSED", "1") != "0" and net.sem_seg_head.in_features == 16 \
+            and net.sem_seg_head.out_features <= 32 and len(oh) == 4 and isinstance(oh[1], nn.BatchNorm1d) \
+            and oh[1].affine and oh[1].track_running_stats and oh[1].momentum is not None \
+            and oh[0].out_features == 16 and oh[3].out_features == 3 and oh[0].bias is not None and oh[3].bias is not None \
+            and net.sem_seg_head.bias is not None
+        self._dense_ws = torch.zeros(80, dtype=torch.float64, device=dev)
         # fused NPCS head + loss (csrc/npcs_loss.cu); GAPART_NPCS_FUSED=0 runs the torch formulation instead
         self.fused_npcs = os.environ.get("GAPART_NPCS_FUSED", "1") != "0" and net.npcs_head.in_features == 16 \
             and net.npcs_head.out_features <= 48
@@ -379,28 +422,20 @@ class FusedTrainStep:
             e.training = net.training
         self.flat_grad.zero_()
         self.batch_indices.copy_(torch.bucketize(self._arangeN, eng.batch_offsets[1:], right=True))
-        pt_xyz = eng.points[:, :3]
         anchor = torch.zeros((), device=self.dev, requires_grad=True)
         pc_feature = _BackboneFn.apply(anchor, eng)
 
         # ---- heads + dense losses (model.py:160-226, :493-523) --------------------------------------------------------
-        sem_logits = net.sem_seg_head(pc_feature)
-        sem_preds = torch.argmax(sem_logits.detach(), dim=-1)
         sem_labels, inst = self.sem_labels, self.instance_labels
-        loss_sem = focal_loss_static(sem_logits, sem_labels, 2.0, net.ignore_sem_label) if net.use_sem_focal_loss \
-            else F.cross_entropy(sem_logits, sem_labels, ignore_index=net.ignore_sem_label)
-        if net.use_sem_dice_loss:
-            loss_sem = loss_sem + dice_loss_static(sem_logits, sem_labels)
-        correct = sem_preds == sem_labels
-        all_accu = correct.float().mean()
-        pixel_accu = _masked_mean(correct.float(), sem_labels > 0)
-        offsets = net.offset_head(pc_feature)
-        gt_off = self.instance_centers - pt_xyz
-        valid = (sem_labels > 0) & (inst >= 0)
-        loss_dist = _masked_mean((offsets - gt_off).abs().sum(-1), valid)
-        gt_dir = gt_off / (torch.norm(gt_off, p=2, dim=-1)[:, None] + 1e-8)
-        pr_dir = offsets / (torch.norm(offsets, p=2, dim=-1)[:, None] + 1e-8)
-        loss_dir = _masked_mean(-(gt_dir * pr_dir).sum(-1), valid)
+        if self.fused_dense and net.training:
+            oh = net.offset_head
+            loss_dense, sem_preds, sem_logits, offsets, sc = _DenseHeads.apply(
+                pc_feature, net.sem_seg_head.weight, net.sem_seg_head.bias, oh[0].weight, oh[0].bias, oh[1].weight, oh[1].bias,
+                oh[3].weight, oh[3].bias, self)
+            loss_sem, loss_dist, loss_dir, all_accu, pixel_accu = sc[0], sc[1], sc[2], sc[3], sc[4]
+        else:
+            loss_dense, sem_preds, sem_logits, offsets, loss_sem, loss_dist, loss_dir, all_accu, pixel_accu = \
+                self._dense_heads_torch(pc_feature)
 
         # ---- proposals (model.py:228-346), sync-free -------------------------------------------------------------------
         st.build(eng.points, sem_preds, offsets.detach().contiguous(), inst, eng.batch_offsets, self.rand)
@@ -438,13 +473,37 @@ class FusedTrainStep:
         else:
             loss_npcs = self._npcs_loss_torch(npcs_feats, ppl, pt_mask, sem_preds, begin, end)
 
-        loss = loss_sem + loss_dist + loss_dir + loss_score + loss_npcs
+        loss = loss_dense + loss_score + loss_npcs
         loss.backward()
         self.losses = dict(loss=loss.detach(), loss_sem_seg=loss_sem.detach(), loss_offset_dist=loss_dist.detach(),
                            loss_offset_dir=loss_dir.detach(), loss_prop_score=loss_score.detach(),
                            loss_prop_npcs=loss_npcs.detach(), all_accu=all_accu, pixel_accu=pixel_accu)
         self.debug = dict(sem_logits=sem_logits.detach(), offsets=offsets.detach(), sem_preds=sem_preds,
                           score_logits_all=score_logits_all.detach(), ious=ious, pc_feature=pc_feature.detach())
+
+    def _dense_heads_torch(self, pc_feature):
+        """the torch formulation of the two dense heads and their losses (reference of the fused kernels; eval mode)"""
+        net, eng = self.net, self.engine
+        pt_xyz = eng.points[:, :3]
+        sem_logits = net.sem_seg_head(pc_feature)
+        sem_preds = torch.argmax(sem_logits.detach(), dim=-1)
+        sem_labels, inst = self.sem_labels, self.instance_labels
+        loss_sem = focal_loss_static(sem_logits, sem_labels, 2.0, net.ignore_sem_label) if net.use_sem_focal_loss \
+            else F.cross_entropy(sem_logits, sem_labels, ignore_index=net.ignore_sem_label)
+        if net.use_sem_dice_loss:
+            loss_sem = loss_sem + dice_loss_static(sem_logits, sem_labels)
+        correct = sem_preds == sem_labels
+        all_accu = correct.float().mean()
+        pixel_accu = _masked_mean(correct.float(), sem_labels > 0)
+        offsets = net.offset_head(pc_feature)
+        gt_off = self.instance_centers - pt_xyz
+        valid = (sem_labels > 0) & (inst >= 0)
+        loss_dist = _masked_mean((offsets - gt_off).abs().sum(-1), valid)
+        gt_dir = gt_off / (torch.norm(gt_off, p=2, dim=-1)[:, None] + 1e-8)
+        pr_dir = offsets / (torch.norm(offsets, p=2, dim=-1)[:, None] + 1e-8)
+        loss_dir = _masked_mean(-(gt_dir * pr_dir).sum(-1), valid)
+        loss_dense = loss_sem + loss_dist + loss_dir
+        return loss_dense, sem_preds, sem_logits, offsets, loss_sem, loss_dist, loss_dir, all_accu, pixel_accu
 
     def _npcs_loss_torch(self, npcs_feats, ppl, pt_mask, sem_preds, begin, end):
         """the static-shape torch formulation of npcs_head + loss_proposal_npcs (reference of the fused kernels)"""

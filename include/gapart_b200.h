@@ -261,6 +261,26 @@ int gp_linear_ce(const float* F, int ldf, int C, const int64_t* labels, int N, c
                  long long ignore_index, float* logits_out, int ldl, float* dF, int lddf, float* dW, float* db,
                  double* loss, int* d_count_ws, void* stream);
 
+/* The two dense per-point heads of the train step with their losses, forward AND backward (GAPartNet.forward_sem_seg /
+ * loss_sem_seg, gapartnet/network/model.py:160-191 with focal_loss / dice_loss of network/losses.py:35-64,132-158;
+ * forward_offset / loss_offset, model.py:193-226):
+ *   sem:    logits = F Wsem^T + bsem (Wsem [K,16]); sem_preds = argmax (first maximum); loss_sem = focal(gamma 2) if
+ *           use_focal else cross-entropy, mean over labels != ignore_index, + (use_dice) the per-point soft dice, mean over N
+ *   offset: off = W2 relu(BN(W1 F + b1)) + b2 with BatchNorm1d batch statistics (eps; running_mean / running_var advanced
+ *           with `momentum`, unbiased variance); loss_dist / loss_dir over points with sem_label > 0 and instance_label >= 0,
+ *           gt = instance_centers - xyz
+ * scalars[0..5] = loss_sem, loss_dist, loss_dir, all_accu, pixel_accu, loss_sem + loss_dist + loss_dir (device floats).
+ * Gradients of scalars[5]: dF [N,16] is overwritten; dWsem [K,16], dbsem [K], dW1 [16,16], db1, dgamma, dbeta [16], dW2 [3,16],
+ * db2 [3] are ACCUMULATED into.  sem_logits (optional) [N, ldl]; offsets [N,3]; ws: 80 doubles of scratch. */
+int gp_dense_heads_fwd_bwd(const float* F, int ldf, int C, int N, const float* Wsem, const float* bsem, int K,
+                           const float* W1, const float* b1, const float* gamma, const float* beta, float eps,
+                           float momentum, float* running_mean, float* running_var, const float* W2, const float* b2,
+                           const int64_t* sem_labels, long long ignore_index, const int* instance_labels,
+                           const float* instance_centers, const float* xyz, int ldxyz, int use_focal, int use_dice,
+                           double* ws, int64_t* sem_preds, float* sem_logits, int ldl, float* offsets, float* scalars,
+                           float* dF, int lddf, float* dWsem, float* dbsem, float* dW1, float* db1, float* dgamma,
+                           float* dbeta, float* dW2, float* db2, void* stream);
+
 /* NPCS head + symmetry-aware NPCS loss over the proposal points (GAPartNet.forward_proposal_npcs / loss_proposal_npcs,
  * gapartnet/network/model.py:387-462; compute_npcs_loss, gapartnet/network/grouping_utils.py:14-43), static shapes:
  *   F [cap_rows, C = 16] per proposal-point features of the NPCS U-Net, rows in proposal (CSR) order; W [K,16], bias [K]
