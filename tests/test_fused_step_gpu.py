@@ -41,9 +41,15 @@ def _relL2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-300))
 
 
-def test_fused_step_matches_the_reference_step(cuda, gold):
+@pytest.mark.parametrize("fused_losses", ["1", "0"])
+def test_fused_step_matches_the_reference_step(cuda, gold, monkeypatch, fused_losses):
+    """fused_losses = "1": dense heads and NPCS head + loss on the fused kernels (dense_heads.cu, npcs_loss.cu);
+    "0": their torch formulations (the eval-mode path) - both against the reference's own step"""
+    monkeypatch.setenv("GAPART_DENSE_FUSED", fused_losses)
+    monkeypatch.setenv("GAPART_NPCS_FUSED", fused_losses)
     g, cfg = gold
     net, fs, batch = _fused(cuda, cfg, use_graph=False)
+    assert fs.fused_dense == (fused_losses == "1") and fs.fused_npcs == (fused_losses == "1")
     fs.load(batch, rand=torch.from_numpy(g["rand"]).to(cuda))
     fs.forward_backward()
     torch.cuda.synchronize()
