@@ -13,6 +13,8 @@ What is restated and from where (paths relative to /root/reference):
                 torch.nn.functional.conv3d second opinion
   cluster.py    epic_ops ball_query / ccl / reduce / iou / nms call contracts
                 (gapartnet/network/grouping_utils.py:108-140,221-245; network/model.py:348-385)
+  losses.py     the heads and loss functions of gapartnet/network/model.py:160-226,396-462, network/losses.py and
+                grouping_utils.py:14-43 (PINNED against the reference's own functions: tests/golden/losses.npz)
   pointnet2.c   serial C restatement of dataset/process_tools/utils/pointnet_lib/src/*_gpu.cu
   _ref/         the reference's OWN pointnet2 CUDA kernels compiled from where they lie
                 (Makefile), callable on the GPU box as a second oracle for row a17

@@ -2,11 +2,11 @@
 offset_head = Linear -> BatchNorm1d (batch statistics) -> ReLU -> Linear + loss_offset_dist / loss_offset_dir, forward and
 backward) against (1) tests/golden/losses.npz = the REFERENCE's own GAPartNet.loss_sem_seg / loss_offset
 (gapartnet/network/model.py:160-226, losses.py) with torch autograd on the same seeded inputs
-(tests/golden/make_golden_losses.py) and (2) FusedTrainStep._dense_heads_torch, the same arithmetic with masks over static
-shapes, in fp64 (pinned against the fixture on the CPU by tests/test_golden_losses_cpu.py): the five scalars, predictions,
+(tests/golden/make_golden_losses.py) and (2) oracle/losses.py, the restatement of those functions, in fp64 (pinned against
+the fixture on the CPU by tests/test_golden_losses_cpu.py): the five scalars, predictions,
 logits, offsets, the gradient w.r.t. the point features and all eight parameter tensors, the BatchNorm running statistics.
 One more case has ignored labels together with the dice loss (the reference's dice_loss cannot take ignore_index at all; the
-kernels clamp such labels to class 0 like the torch formulation)."""
+kernels count such labels as class 0, as the oracle's extension does)."""
 import os
 
 import numpy as np
@@ -14,6 +14,8 @@ import pytest
 import torch
 
 from gapartnet_b200.network import fused_step as fsm
+
+from oracle import losses as ol
 
 import util
 from util import rel_err
@@ -54,28 +56,33 @@ def check(case, focal, dice, n, out, gold):
                 assert rel_err(gr, g(gold[k + "grad/" + name]) * GOUT) < 1e-4, name
         assert rel_err(out["running_mean"], g(gold[k + "running_mean"])) < 1e-5
         assert rel_err(out["running_var"], g(gold[k + "running_var"])) < 1e-5
-    # (2) the torch formulation in fp64
-    ref, rstep = util.dense_heads_namespace(case, focal, dice, dtype=torch.float64, device=dev)
-    f64 = torch.from_numpy(case["feat"]).double().to(dev).requires_grad_(True)
-    r_loss, r_preds, r_logits, r_off, r_sem, r_dist, r_dir, r_all, r_pix = fsm.FusedTrainStep._dense_heads_torch(rstep, f64)
-    (r_loss * GOUT).backward()
+    # (2) the oracle's restatement in fp64
+    t64 = lambda a: torch.from_numpy(a).double().to(dev)
+    rp = {name: t64(v).requires_grad_(True) for name, v in case["params"].items()}
+    f64 = t64(case["feat"]).requires_grad_(True)
+    r = ol.dense_heads(f64, rp, t64(case["points"]), torch.from_numpy(case["labels"]).to(dev),
+                       torch.from_numpy(case["inst"]).to(dev), t64(case["centers"]), focal, dice)
+    (r["loss"] * GOUT).backward()
     sc = out["scalars"]
-    for got, want in ((sc[0], r_sem), (sc[1], r_dist), (sc[2], r_dir), (sc[3], r_all), (sc[4], r_pix), (out["loss"], r_loss)):
-        assert abs(float(got) - float(want.detach())) < 2e-6 * max(1.0, abs(float(want.detach()))), (float(got), float(want.detach()))
-    assert torch.equal(out["preds"], r_preds)
-    assert rel_err(out["logits"], r_logits) < 1e-5 and rel_err(out["offsets"], r_off) < 1e-5
+    for got, want in ((sc[0], r["loss_sem"]), (sc[1], r["loss_dist"]), (sc[2], r["loss_dir"]), (sc[3], r["all_accu"]),
+                      (sc[4], r["pixel_accu"]), (out["loss"], r["loss"])):
+        want = float(want.detach())
+        assert abs(float(got) - want) < 2e-6 * max(1.0, abs(want)), (float(got), want)
+    assert torch.equal(out["preds"], r["sem_preds"])
+    assert rel_err(out["logits"], r["sem_logits"]) < 1e-5 and rel_err(out["offsets"], r["offsets"]) < 1e-5
     assert rel_err(out["d_feat"], f64.grad) < 5e-5
-    rgrads = {"sem_seg_head." + a: p.grad for a, p in ref.sem_seg_head.named_parameters()}
-    rgrads.update({"offset_head." + a: p.grad for a, p in ref.offset_head.named_parameters()})
     for name, gr in out["grads"].items():
         if name == "offset_head.0.bias":
             # the bias in front of a BatchNorm has no gradient (the batch mean removes it): rounding noise on both sides
             assert float(gr.abs().max()) < 1e-6 * float(out["grads"]["offset_head.0.weight"].abs().max())
-            assert float(rgrads[name].abs().max()) < 1e-12
+            assert float(rp[name].grad.abs().max()) < 1e-12
         else:
-            assert rel_err(gr, rgrads[name]) < 5e-5, name
-    rbn = ref.offset_head[1]
-    assert rel_err(out["running_mean"], rbn.running_mean) < 1e-5 and rel_err(out["running_var"], rbn.running_var) < 1e-5
+            assert rel_err(gr, rp[name].grad) < 5e-5, name
+    # running statistics (torch: momentum 0.1 from (0, 1), unbiased variance) from the oracle's hidden layer
+    with torch.no_grad():
+        h = torch.nn.functional.linear(f64, rp["offset_head.0.weight"], rp["offset_head.0.bias"])
+        assert rel_err(out["running_mean"], 0.1 * h.mean(0)) < 1e-5
+        assert rel_err(out["running_var"], 0.9 + 0.1 * h.var(0, unbiased=True)) < 1e-5
     assert out["batches"] == 1
 
 

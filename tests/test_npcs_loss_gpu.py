@@ -1,8 +1,8 @@
 """GPU: the fused NPCS head + symmetry-aware NPCS loss kernels (gp_npcs_loss_fwd / gp_npcs_loss_bwd, csrc/npcs_loss.cu)
 against (1) tests/golden/losses.npz = the REFERENCE's own GAPartNet.loss_proposal_npcs + compute_npcs_loss
 (gapartnet/network/model.py:396-462, grouping_utils.py:14-43) with torch autograd on the same seeded inputs
-(tests/golden/make_golden_losses.py) and (2) `_reference` below, the same formulation in fp64 (pinned against the fixture on
-the CPU by tests/test_golden_losses_cpu.py).  Cases (tests/util.py npcs_case): proposals with one class each (the train
+(tests/golden/make_golden_losses.py) and (2) oracle/losses.py, the restatement of those functions, in fp64 (pinned against
+the fixture on the CPU by tests/test_golden_losses_cpu.py).  Cases (tests/util.py npcs_case): proposals with one class each (the train
 step's situation) and rows of mixed classes inside a proposal (segments of the warp reduction split), proposal lengths from
 1 row to many warps, dead rows behind the device count, a non-unit upstream gradient."""
 import os
@@ -13,33 +13,14 @@ import torch
 
 from gapartnet_b200.misc.info import DEFAULT_SYMMETRY_INDICES, get_symmetry_matrix
 
+from oracle import losses as ol
+
 import util
 from util import rel_err
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses.npz")
 GOUT = 0.7          # upstream gradient handed to the backward kernel
-
-
-def _reference(feats, W, b, pp, pidx, sem_preds, sem_labels, gt_all, sym_idx, mats):
-    """loss_proposal_npcs + compute_npcs_loss of the reference on the live rows (dtype of the inputs)"""
-    logits = feats @ W.t() + b
-    sp, sl, gt = sem_preds[pp], sem_labels[pp], gt_all[pp]
-    valid = (sp == sl) & (gt != 0).any(-1)
-    logits, gt, sp, pidx = logits[valid], gt[valid], sp[valid], pidx[valid]
-    npcs = logits.view(logits.shape[0], -1, 3).gather(1, (sp - 1)[:, None, None].expand(-1, 1, 3)).squeeze(1)
-    sym = sym_idx[sp]
-    loss = feats.new_zeros(())
-    for mask, M, base in ((sym < 3, mats[0], 0), (sym == 3, mats[1], 3), (sym == 4, mats[2], 4)):
-        if int(mask.sum()) == 0:
-            continue
-        _, counts = torch.unique_consecutive(pidx[mask], return_counts=True)
-        g = (gt[mask][:, None, None, :] @ M[sym[mask] - base]).squeeze(2)
-        d2 = ((npcs[mask][:, None, :] - g - 0.5) ** 2).sum(-1)
-        l = torch.where(d2 <= 0.01, 5 * d2, torch.sqrt(d2) - 0.05)
-        seg = torch.segment_reduce(l, "mean", lengths=counts)
-        loss = loss + seg.min(-1)[0].mean()
-    return loss
 
 
 def run_kernels(c, dev):
@@ -88,7 +69,7 @@ def check(c, mixed, loss, dF, dW, db, gold):
     sym_idx = torch.as_tensor(DEFAULT_SYMMETRY_INDICES, dtype=torch.int64, device=dev)
     mats = [m.to(dev).double() for m in get_symmetry_matrix()]
     d_sp, d_pp = t(c["sem_preds"]), t(c["pp"]).long()
-    ref = _reference(rf, rW, rb, d_pp, t(c["pidx"]).long(), d_sp, t(c["sem_labels"]), t(c["gt"]).double(), sym_idx, mats)
+    ref = ol.npcs_head_loss(rf, rW, rb, d_pp, t(c["pidx"]).long(), d_sp, t(c["sem_labels"]), t(c["gt"]).double(), sym_idx, mats)
     (ref * GOUT).backward()
     assert abs(float(loss) - float(ref.detach())) < 2e-6 * max(1.0, abs(float(ref.detach())))
     assert rel_err(dF[:NP], rf.grad) < 2e-5
