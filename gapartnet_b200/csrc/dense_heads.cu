@@ -376,7 +376,6 @@ __global__ void __launch_bounds__(DH_THREADS) k_dh_bwd(DhArgs a) {
     __shared__ float sW1[DH_C * DH_C], sb1[DH_C], sW2[3 * DH_C], sb2[4];
     __shared__ float s_mean[DH_C], s_istd[DH_C], s_gamma[DH_C], s_beta[DH_C], s_mdz[DH_C], s_mdzx[DH_C];
     __shared__ float sF[DH_THREADS][DH_C + 1], sD[DH_THREADS][DH_C + 1];
-    __shared__ float s_redf[DH_THREADS / 32];
     const int tid = threadIdx.x;
     for (int i = tid; i < DH_C * DH_C; i += DH_THREADS) sW1[i] = a.W1[i];
     for (int i = tid; i < 3 * DH_C; i += DH_THREADS) sW2[i] = a.W2[i];
@@ -450,7 +449,6 @@ __global__ void __launch_bounds__(DH_THREADS) k_dh_bwd(DhArgs a) {
         atomicAdd(a.dW1 + tid + DH_THREADS, accW[1]);
     }
     if (tid < DH_C && a.db1) atomicAdd(a.db1 + tid, accB);
-    (void)s_redf;
 }
 
 // scalars out[0..5] = loss_sem, loss_dist, loss_dir, all_accu, pixel_accu, loss_sem + loss_dist + loss_dir;
